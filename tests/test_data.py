@@ -1,0 +1,77 @@
+"""Data pipeline (untested in the reference)."""
+import io
+import tarfile
+
+import numpy as np
+import pytest
+import torch
+
+from zero_transformer_b200.data.pipeline import (DevicePrefetcher, StreamingTokenDataset, SyntheticTokenDataset,
+                                                 batch_iterator, read_index, rechunk, split_by_rank, to_micro_batches)
+
+
+def _write_shards(tmp_path, n_shards=4, rows=10, ctx=16):
+    names = []
+    for s in range(n_shards):
+        arr = (np.arange(rows * ctx).reshape(rows, ctx) + 1000 * s).astype(np.int32)
+        p = tmp_path / f"shard{s}.npy"
+        np.save(p, arr)
+        names.append(p.name)
+    idx = tmp_path / "train.index"
+    idx.write_text("# comment\n" + "\n".join(names) + "\n\n")
+    return str(idx)
+
+
+def test_index_and_rank_striding(tmp_path):
+    idx = _write_shards(tmp_path)
+    shards = read_index(idx)
+    assert len(shards) == 4 and all(s.endswith(".npy") for s in shards)
+    assert split_by_rank(shards, 1, 2) == shards[1::2]
+    a = {int(r[0]) for r in StreamingTokenDataset(idx, max_context=16, rank=0, world=2, shuffle_buffer=4)}
+    b = {int(r[0]) for r in StreamingTokenDataset(idx, max_context=16, rank=1, world=2, shuffle_buffer=4)}
+    assert len(a) == len(b) == 20 and not (a & b)
+
+
+def test_shuffle_is_seeded(tmp_path):
+    idx = _write_shards(tmp_path)
+    f = lambda seed: [int(r[0]) for r in StreamingTokenDataset(idx, max_context=16, shuffle_buffer=8, seed=seed)]
+    assert f(23) == f(23) and f(23) != f(24) and sorted(f(23)) == sorted(f(24))
+
+
+def test_tar_shard_with_pth_members_and_corrupt_sample(tmp_path):
+    p = tmp_path / "s.tar"
+    with tarfile.open(p, "w") as tf:
+        for i in range(3):
+            buf = io.BytesIO()
+            torch.save(torch.arange(20) + i, buf)
+            data = buf.getvalue()
+            ti = tarfile.TarInfo(f"{i:06d}.input_id.pth")
+            ti.size = len(data)
+            tf.addfile(ti, io.BytesIO(data))
+        bad = b"not a tensor"
+        ti = tarfile.TarInfo("bad.input_id.pth")
+        ti.size = len(bad)
+        tf.addfile(ti, io.BytesIO(bad))
+    (tmp_path / "v.index").write_text("s.tar\n")
+    rows = list(StreamingTokenDataset(str(tmp_path / "v.index"), max_context=16, shuffle_buffer=1))
+    assert len(rows) == 3 and rows[0].shape == (16,) and rows[0].dtype == np.int32
+
+
+def test_rechunk_and_micro_batches():
+    b = torch.arange(4 * 8).view(4, 8)
+    r = rechunk(b, 4)
+    assert r.shape == (8, 4) and torch.equal(r[1], torch.tensor([4, 5, 6, 7]))
+    mb = to_micro_batches(r, 2)
+    assert mb.shape == (2, 4, 4)
+    with pytest.raises(AssertionError):
+        to_micro_batches(r, 3)
+
+
+def test_synthetic_is_deterministic_and_prefetcher_runs():
+    a = [x.copy() for _, x in zip(range(3), SyntheticTokenDataset(100, 8, rank=0, seed=1))]
+    b = [x.copy() for _, x in zip(range(3), SyntheticTokenDataset(100, 8, rank=0, seed=1))]
+    c = [x.copy() for _, x in zip(range(3), SyntheticTokenDataset(100, 8, rank=1, seed=1))]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and not np.array_equal(a[0], c[0])
+    pf = DevicePrefetcher(batch_iterator(SyntheticTokenDataset(100, 8, length=10), 4), "cpu")
+    got = list(pf)
+    assert len(got) == 2 and got[0].shape == (4, 8) and got[0].max() < 100

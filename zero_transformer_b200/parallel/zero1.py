@@ -1,0 +1,298 @@
+"""ZeRO stage-1 engine: replicated low-precision parameters for compute,
+fp32 master weights + Adam moments sharded 1/world per rank.
+
+What the reference does (``main_zero.py:443-460,495-500``,
+``src/partitioning/xmap_train_functions.py:26-123``): ``pmean`` the full gradient
+(all-reduce), slice it to per-device shards, run AdamW on 1/n of every tensor,
+and let XLA all-gather the updated *fp32* parameters.  What this engine does per
+optimizer step:
+
+    reduce-scatter(grads)  ->  clip/scale + AdamW on the owned shard (fp32
+    master, m, v)  ->  write the updated shard in the compute dtype  ->
+    all-gather(params)
+
+with three interchangeable communication backends:
+
+``fused``      hand-written sm_100a kernels over NVLink peer memory: the
+               reduce-scatter is fused with cast/scale/clip/AdamW and emits the
+               bf16 shard; the all-gather is a P2P pull (optionally fused into
+               the first consuming GEMM).  No NCCL call.  (``parallel/fused.py``)
+``nccl``       ``reduce_scatter_tensor`` + ``all_gather_into_tensor`` per region
+               (works on gloo for the CPU plumbing tests as well).
+``allreduce``  the reference's own pattern: all-reduce, slice, all-gather.
+
+The engine owns the flat buffers; model parameters (and their ``.grad``) are
+re-pointed to views of them, so backward accumulates straight into the
+communication buffer (no copy-in), and ``step()`` never walks Python lists of
+tensors on the hot path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..ops import reference
+from .layout import FlatLayout, default_bucket_of
+
+
+def _dist_info(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+class Zero1Engine:
+    def __init__(
+        self,
+        model: torch.nn.Module,
+        *,
+        lr_fn: Callable[[int], float],
+        weight_decay: float = 0.1,
+        betas=(0.9, 0.95),
+        eps: float = 1e-8,
+        clip: Optional[float] = 1.0,
+        grad_accum_steps: int = 1,
+        group=None,
+        backend: str = "auto",
+        compute_dtype: Optional[torch.dtype] = None,
+        grad_dtype: Optional[torch.dtype] = None,
+        decay_mask: Optional[Dict[str, bool]] = None,
+        bucket_of=default_bucket_of,
+    ):
+        self.model = model
+        self.group = group
+        self.rank, self.world = _dist_info(group)
+        self.lr_fn = lr_fn
+        self.weight_decay = float(weight_decay)
+        self.beta1, self.beta2 = float(betas[0]), float(betas[1])
+        self.eps = float(eps)
+        self.clip = clip
+        self.grad_accum_steps = int(grad_accum_steps)
+        self.step_count = 0  # optimizer updates applied so far
+
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        if not named:
+            raise ValueError("model has no trainable parameters")
+        dev = named[0][1].device
+        self.device = dev
+        src_dtype = named[0][1].dtype
+        self.compute_dtype = compute_dtype or (torch.bfloat16 if dev.type == "cuda" else src_dtype)
+        self.grad_dtype = grad_dtype or self.compute_dtype
+        if decay_mask is None:
+            decay_mask = model.decay_mask() if hasattr(model, "decay_mask") else {n: p.ndim >= 2 for n, p in named}
+        self.layout = FlatLayout([(n, tuple(p.shape)) for n, p in named], decay_mask, self.world, bucket_of)
+        L = self.layout
+
+        if backend == "auto":
+            backend = "fused" if dev.type == "cuda" else "nccl"
+        if backend not in ("fused", "nccl", "allreduce"):
+            raise ValueError(f"unknown comm backend '{backend}'")
+        self.backend = backend
+        self._fused = None
+        if backend == "fused":
+            from .fused import FusedComm  # needs the CUDA extension; fails loudly without it
+
+            self._fused = FusedComm(L, self.rank, self.world, group, dev, self.compute_dtype, self.grad_dtype)
+            self.flat_param = self._fused.flat_param
+            self.flat_grad = self._fused.flat_grad
+        else:
+            self.flat_param = torch.zeros(L.total, dtype=self.compute_dtype, device=dev)
+            self.flat_grad = torch.zeros(L.total, dtype=self.grad_dtype, device=dev)
+
+        # fp32 master shard taken from the (ideally fp32-initialised) model, then the
+        # model is re-pointed at the low-precision flat buffer.
+        self.master = torch.zeros(L.shard_total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.master)
+        self.exp_avg_sq = torch.zeros_like(self.master)
+        self.decay_vec = L.decay_mask_shard(dev)
+        with torch.no_grad():
+            for n, p in named:
+                r = L.by_name[n]
+                full = torch.zeros(r.padded, dtype=torch.float32, device=dev)
+                full[: r.numel].copy_(p.detach().reshape(-1).float())
+                s = self.rank * r.chunk
+                self.master[r.shard_offset: r.shard_offset + r.chunk].copy_(full[s: s + r.chunk])
+                self.flat_param[r.offset: r.offset + r.padded].copy_(full.to(self.compute_dtype))
+                p.data = L.view(self.flat_param, n)
+                p.grad = L.view(self.flat_grad, n)
+        self._named = named
+        self._grad_shard = torch.zeros(L.shard_total, dtype=self.grad_dtype, device=dev) if backend != "fused" else None
+
+    # ------------------------------------------------------------------
+    @property
+    def lr(self) -> float:
+        return float(self.lr_fn(self.step_count))
+
+    def zero_grad(self) -> None:
+        self.flat_grad.zero_()
+        # autograd may have replaced .grad if someone set it to None; re-point cheaply
+        for n, p in self._named:
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + self.layout.by_name[n].offset * self.flat_grad.element_size():
+                p.grad = self.layout.view(self.flat_grad, n)
+
+    # ------------------------------------------------------------------
+    def step(self) -> float:
+        """Apply one optimizer update from the gradients accumulated in
+        ``flat_grad`` (sum over micro-batches of per-micro-batch mean-loss
+        gradients).  Returns the learning rate used."""
+        lr = self.lr
+        t = self.step_count + 1
+        scale = 1.0 / (self.world * self.grad_accum_steps)
+        if self.backend == "fused":
+            self._fused.step(
+                master=self.master, m=self.exp_avg, v=self.exp_avg_sq,
+                lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps, wd=self.weight_decay,
+                step=t, clip=self.clip or 0.0, grad_scale=scale,
+            )
+        else:
+            self._reduce_to_shard()
+            with torch.no_grad():
+                reference.adamw_step_(
+                    self.master, self._grad_shard, self.exp_avg, self.exp_avg_sq,
+                    lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps,
+                    wd=self.decay_vec * self.weight_decay, step=t, clip=self.clip, grad_scale=scale,
+                )
+                self.layout.scatter_shard_to_flat(self.master.to(self.compute_dtype), self.flat_param, self.rank)
+            self._all_gather_params()
+        self.step_count += 1
+        return lr
+
+    # -- unfused collectives --------------------------------------------
+    def _reduce_to_shard(self) -> None:
+        L = self.layout
+        if self.world == 1:
+            L.gather_shard_from_flat(self.flat_grad, 0, self._grad_shard)
+            return
+        if self.backend == "allreduce":
+            # reference pattern (xmap_train_functions.py:84 + main_zero.py:497): all-reduce, then local slice
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            L.gather_shard_from_flat(self.flat_grad, self.rank, self._grad_shard)
+            return
+        for r in L.regions:
+            out = self._grad_shard[r.shard_offset: r.shard_offset + r.chunk]
+            dist.reduce_scatter_tensor(out, self.flat_grad[r.offset: r.offset + r.padded], op=dist.ReduceOp.SUM, group=self.group)
+
+    def _all_gather_params(self) -> None:
+        if self.world == 1:
+            return
+        L = self.layout
+        inplace_ok = self.flat_param.is_cuda  # NCCL supports in-place all-gather; gloo gets a staging copy
+        for r in L.regions:
+            s, e = r.chunk_range(self.rank)
+            src = self.flat_param[s:e] if inplace_ok else self.flat_param[s:e].clone()
+            dist.all_gather_into_tensor(self.flat_param[r.offset: r.offset + r.padded], src, group=self.group)
+
+    # -- state -----------------------------------------------------------
+    def shard_state(self) -> Dict[str, object]:
+        """This rank's optimizer shard (what the reference keeps sharded on
+        device, ``main_zero.py:447-450``)."""
+        return {
+            "step": self.step_count, "rank": self.rank, "world": self.world,
+            "master": self.master.detach().cpu(), "exp_avg": self.exp_avg.detach().cpu(),
+            "exp_avg_sq": self.exp_avg_sq.detach().cpu(),
+        }
+
+    def load_shard_state(self, st: Dict[str, object]) -> None:
+        if int(st["world"]) != self.world or int(st["rank"]) != self.rank:
+            raise ValueError("shard state belongs to a different (rank, world); load a consolidated state instead")
+        self.step_count = int(st["step"])
+        self.master.copy_(st["master"])
+        self.exp_avg.copy_(st["exp_avg"])
+        self.exp_avg_sq.copy_(st["exp_avg_sq"])
+        self._push_master_to_params()
+
+    def consolidated_state(self, dst: int = 0) -> Optional[Dict[str, object]]:
+        """Gather the sharded state into full per-parameter fp32 tensors on
+        ``dst`` (the reference gathers with ``process_allgather`` before saving,
+        ``main_zero.py:554-557``).  World-size independent, so a run can resume
+        on a different number of GPUs."""
+        L = self.layout
+        out = {"step": self.step_count, "params": {}, "exp_avg": {}, "exp_avg_sq": {}}
+        for key, shard in (("params", self.master), ("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
+            if self.world > 1:
+                parts = [torch.empty_like(shard) for _ in range(self.world)]
+                dist.all_gather(parts, shard, group=self.group)
+            else:
+                parts = [shard]
+            if self.rank == dst or self.world == 1:
+                for r in L.regions:
+                    full = torch.cat([pt[r.shard_offset: r.shard_offset + r.chunk] for pt in parts])
+                    out[key][r.name] = full[: r.numel].view(r.shape).cpu().clone()
+        return out if (self.rank == dst or self.world == 1) else None
+
+    def load_consolidated_state(self, st: Dict[str, object], load_moments: bool = True, adopt_step: bool = True) -> None:
+        L = self.layout
+        with torch.no_grad():
+            for key, shard in (("params", self.master), ("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
+                if key != "params" and (not load_moments or key not in st):
+                    continue
+                for r in L.regions:
+                    full = torch.zeros(r.padded, dtype=torch.float32)
+                    full[: r.numel].copy_(st[key][r.name].reshape(-1).float())
+                    s = self.rank * r.chunk
+                    shard[r.shard_offset: r.shard_offset + r.chunk].copy_(full[s: s + r.chunk])
+        if adopt_step:
+            self.step_count = int(st.get("step", 0))
+        self._push_master_to_params(full_params=st["params"])
+
+    def _push_master_to_params(self, full_params: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        with torch.no_grad():
+            if full_params is not None:
+                for r in self.layout.regions:
+                    self.flat_param[r.offset: r.offset + r.numel].copy_(full_params[r.name].reshape(-1).to(self.compute_dtype))
+                return
+            self.layout.scatter_shard_to_flat(self.master.to(self.compute_dtype), self.flat_param, self.rank)
+            if self.backend == "fused":
+                self._fused.all_gather_now()
+            else:
+                self._all_gather_params()
+
+    def full_params_fp32(self, dst: int = 0):
+        st = self.consolidated_state(dst)
+        return None if st is None else st["params"]
+
+    def memory_report(self) -> str:
+        gb = 1.0 / (1 << 30)
+        L = self.layout
+        pb = L.total * self.flat_param.element_size()
+        gbs = L.total * self.flat_grad.element_size()
+        ob = 3 * L.shard_total * 4
+        return (f"ZeRO-1 rank {self.rank}/{self.world} [{self.backend}]: params {pb * gb:.2f} GiB ({self.compute_dtype}), "
+                f"grads {gbs * gb:.2f} GiB ({self.grad_dtype}), fp32 master+m+v shard {ob * gb:.2f} GiB "
+                f"(unsharded would be {ob * self.world * gb:.2f} GiB)")
+
+
+class PlainAdamW:
+    """Unsharded fp32 AdamW with the same math (elementwise clip -> AdamW with
+    ``ndim >= 2`` decay mask).  The oracle for the ZeRO-1 equivalence tests and
+    the optimizer of the single-process reference arm."""
+
+    def __init__(self, model, *, lr_fn, weight_decay=0.1, betas=(0.9, 0.95), eps=1e-8, clip=1.0, grad_accum_steps=1, world=1):
+        self.params = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        self.lr_fn = lr_fn
+        self.wd, self.b1, self.b2, self.eps, self.clip = weight_decay, betas[0], betas[1], eps, clip
+        self.scale = 1.0 / (grad_accum_steps * world)
+        self.m = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in self.params}
+        self.v = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in self.params}
+        self.master = {n: p.detach().float().clone() for n, p in self.params}
+        self.step_count = 0
+
+    def zero_grad(self):
+        for _, p in self.params:
+            p.grad = None
+
+    def step(self) -> float:
+        lr = float(self.lr_fn(self.step_count))
+        t = self.step_count + 1
+        with torch.no_grad():
+            for n, p in self.params:
+                if p.grad is None:
+                    continue
+                reference.adamw_step_(self.master[n], p.grad, self.m[n], self.v[n], lr=lr, beta1=self.b1, beta2=self.b2,
+                                      eps=self.eps, wd=self.wd if p.ndim >= 2 else 0.0, step=t, clip=self.clip, grad_scale=self.scale)
+                p.copy_(self.master[n].to(p.dtype))
+        self.step_count += 1
+        return lr
