@@ -1,0 +1,201 @@
+// Python bindings (pybind11 through torch/extension.h).  Thin: argument checks, output
+// allocation, current-stream lookup; all device code lives in the .cu files.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <vector>
+
+#include "launchers.h"
+
+namespace {
+
+void check(int rc, const char* what) {
+  if (rc != 0) throw std::runtime_error(std::string(what) + " failed: " + ztb_last_error());
+}
+cudaStream_t stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+int num_sms() {
+  static int n = 0;
+  if (!n) n = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  return n;
+}
+void need(bool c, const char* msg) {
+  if (!c) throw std::invalid_argument(msg);
+}
+bool is_bf16_cuda(const at::Tensor& t) { return t.is_cuda() && t.scalar_type() == at::kBFloat16; }
+
+std::vector<at::Tensor> layernorm_fwd(const at::Tensor& x, const at::Tensor& w, double eps) {
+  need(is_bf16_cuda(x) && is_bf16_cuda(w) && x.is_contiguous() && w.is_contiguous(), "layernorm_fwd: bf16 contiguous CUDA tensors");
+  c10::cuda::CUDAGuard g(x.device());
+  int D = x.size(-1);
+  int M = x.numel() / D;
+  need(D % 8 == 0 && w.numel() == D, "layernorm_fwd: bad D");
+  auto y = at::empty_like(x);
+  auto mean = at::empty({M}, x.options().dtype(at::kFloat));
+  auto rstd = at::empty({M}, x.options().dtype(at::kFloat));
+  check(ztb_layernorm_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(), M, D, (float)eps, stream()), "layernorm_fwd");
+  return {y, mean, rstd};
+}
+
+std::vector<at::Tensor> layernorm_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& w, const at::Tensor& mean,
+                                      const at::Tensor& rstd) {
+  need(is_bf16_cuda(dy) && is_bf16_cuda(x) && dy.is_contiguous() && x.is_contiguous(), "layernorm_bwd: bf16 contiguous");
+  c10::cuda::CUDAGuard g(x.device());
+  int D = x.size(-1);
+  int M = x.numel() / D;
+  auto dx = at::empty_like(x);
+  auto dw = at::empty({D}, x.options().dtype(at::kFloat));
+  check(ztb_layernorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(), dx.data_ptr(),
+                          dw.data_ptr<float>(), M, D, num_sms(), stream()), "layernorm_bwd");
+  return {dx, dw};
+}
+
+at::Tensor dropout_add(const at::Tensor& y, const c10::optional<at::Tensor>& res, double p, const at::Tensor& rng, int64_t op_id) {
+  need(is_bf16_cuda(y) && y.is_contiguous(), "dropout_add: y bf16 contiguous");
+  need(rng.is_cuda() && rng.scalar_type() == at::kLong && rng.numel() >= 2, "dropout_add: rng must be a CUDA int64[2] tensor");
+  c10::cuda::CUDAGuard g(y.device());
+  auto out = at::empty_like(y);
+  const void* r = nullptr;
+  if (res.has_value()) { need(is_bf16_cuda(*res) && res->is_contiguous() && res->numel() == y.numel(), "dropout_add: bad residual"); r = res->data_ptr(); }
+  check(ztb_dropout_add(y.data_ptr(), r, out.data_ptr(), (size_t)y.numel(), (float)p, (const uint64_t*)rng.data_ptr<int64_t>(), (uint32_t)op_id, num_sms(), stream()), "dropout_add");
+  return out;
+}
+
+at::Tensor embedding_fwd(const at::Tensor& idx, const at::Tensor& wte) {
+  need(idx.is_cuda() && idx.scalar_type() == at::kInt && idx.is_contiguous(), "embedding_fwd: idx must be int32 CUDA contiguous");
+  need(is_bf16_cuda(wte) && wte.is_contiguous() && wte.size(1) % 8 == 0, "embedding_fwd: wte bf16 contiguous, D % 8 == 0");
+  c10::cuda::CUDAGuard g(wte.device());
+  auto sizes = idx.sizes().vec();
+  sizes.push_back(wte.size(1));
+  auto out = at::empty(sizes, wte.options());
+  check(ztb_embedding_fwd(idx.data_ptr<int>(), wte.data_ptr(), out.data_ptr(), (int)idx.numel(), (int)wte.size(1), (int)wte.size(0), stream()), "embedding_fwd");
+  return out;
+}
+
+void embedding_bwd_(const at::Tensor& idx, const at::Tensor& dout, at::Tensor& dwte) {
+  need(idx.is_cuda() && idx.scalar_type() == at::kInt && idx.is_contiguous(), "embedding_bwd: idx int32");
+  need(is_bf16_cuda(dout) && dout.is_contiguous() && dwte.is_cuda() && dwte.is_contiguous(), "embedding_bwd: tensors");
+  need(dwte.scalar_type() == at::kBFloat16 || dwte.scalar_type() == at::kFloat, "embedding_bwd: grad dtype");
+  c10::cuda::CUDAGuard g(dout.device());
+  check(ztb_embedding_bwd(idx.data_ptr<int>(), dout.data_ptr(), dwte.data_ptr(), dwte.scalar_type() == at::kFloat, (int)idx.numel(),
+                          (int)dwte.size(1), (int)dwte.size(0), stream()), "embedding_bwd");
+}
+
+at::Tensor gelu_bwd(const at::Tensor& dg, const at::Tensor& z) {
+  need(is_bf16_cuda(dg) && is_bf16_cuda(z) && dg.is_contiguous() && z.is_contiguous() && dg.numel() % 8 == 0, "gelu_bwd: bf16 contiguous, numel % 8 == 0");
+  c10::cuda::CUDAGuard g(z.device());
+  auto dz = at::empty_like(z);
+  check(ztb_gelu_bwd(dg.data_ptr(), z.data_ptr(), dz.data_ptr(), (size_t)z.numel(), num_sms(), stream()), "gelu_bwd");
+  return dz;
+}
+at::Tensor gelu_fwd(const at::Tensor& z) {
+  need(is_bf16_cuda(z) && z.is_contiguous() && z.numel() % 8 == 0, "gelu_fwd: bf16 contiguous, numel % 8 == 0");
+  c10::cuda::CUDAGuard g(z.device());
+  auto o = at::empty_like(z);
+  check(ztb_gelu_fwd(z.data_ptr(), o.data_ptr(), (size_t)z.numel(), num_sms(), stream()), "gelu_fwd");
+  return o;
+}
+
+std::vector<at::Tensor> ce_fwd(const at::Tensor& logits, const at::Tensor& labels) {
+  need(is_bf16_cuda(logits) && logits.dim() == 2 && logits.stride(1) == 1, "ce_fwd: logits must be 2-D bf16 with contiguous rows");
+  need(labels.is_cuda() && labels.scalar_type() == at::kInt && labels.numel() == logits.size(0), "ce_fwd: labels int32 [M]");
+  need(logits.stride(0) % 8 == 0, "ce_fwd: row stride must be a multiple of 8");
+  c10::cuda::CUDAGuard g(logits.device());
+  int M = logits.size(0), V = logits.size(1);
+  auto lse = at::empty({M}, logits.options().dtype(at::kFloat));
+  auto nll = at::empty({M}, logits.options().dtype(at::kFloat));
+  check(ztb_ce_fwd(logits.data_ptr(), labels.data_ptr<int>(), lse.data_ptr<float>(), nll.data_ptr<float>(), M, V, (size_t)logits.stride(0), stream()), "ce_fwd");
+  return {lse, nll};
+}
+void ce_bwd_(at::Tensor& logits, const at::Tensor& labels, const at::Tensor& lse, const at::Tensor& gscale, double inv_count) {
+  need(is_bf16_cuda(logits) && logits.dim() == 2 && logits.stride(1) == 1, "ce_bwd: logits");
+  need(gscale.is_cuda() && gscale.scalar_type() == at::kFloat && gscale.numel() == 1, "ce_bwd: gscale fp32 scalar tensor");
+  c10::cuda::CUDAGuard g(logits.device());
+  check(ztb_ce_bwd(logits.data_ptr(), labels.data_ptr<int>(), lse.data_ptr<float>(), gscale.data_ptr<float>(), (float)inv_count,
+                   (int)logits.size(0), (int)logits.size(1), (size_t)logits.stride(0), stream()), "ce_bwd");
+}
+
+// C[M,N] (+)= op(A) * op(B)^T ; see launchers.h ZtbGemmArgs.  a_mn: A given as [K,M]; b_mn: B given as [K,N].
+at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tensor> C_, int64_t epilogue,
+                const c10::optional<at::Tensor>& aux_in, c10::optional<at::Tensor> aux_out, double p,
+                const c10::optional<at::Tensor>& rng, int64_t op_id, bool accumulate, bool a_mn, bool b_mn) {
+  need(is_bf16_cuda(A) && is_bf16_cuda(B) && A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "gemm: A, B must be 2-D bf16 CUDA with unit inner stride");
+  c10::cuda::CUDAGuard g(A.device());
+  ZtbGemmArgs a{};
+  a.M = a_mn ? A.size(1) : A.size(0);
+  a.K = a_mn ? A.size(0) : A.size(1);
+  a.N = b_mn ? B.size(1) : B.size(0);
+  need((b_mn ? B.size(0) : B.size(1)) == a.K, "gemm: K mismatch");
+  at::Tensor C;
+  if (C_.has_value()) {
+    C = *C_;
+    need(C.is_cuda() && C.dim() == 2 && C.size(0) == a.M && C.size(1) == a.N && C.stride(1) == 1, "gemm: bad C");
+    need(C.scalar_type() == at::kBFloat16 || C.scalar_type() == at::kFloat, "gemm: C dtype");
+  } else {
+    need(!accumulate, "gemm: accumulate needs an explicit C");
+    C = at::empty({a.M, a.N}, A.options());
+  }
+  a.A = A.data_ptr(); a.B = B.data_ptr(); a.C = C.data_ptr();
+  a.lda = A.stride(0); a.ldb = B.stride(0); a.ldc = C.stride(0);
+  a.epilogue = (int)epilogue;
+  a.accumulate = accumulate; a.c_is_fp32 = C.scalar_type() == at::kFloat;
+  a.a_mn_major = a_mn; a.b_mn_major = b_mn;
+  a.p = (float)p; a.op_id = (uint32_t)op_id;
+  if (aux_in.has_value()) {
+    need(is_bf16_cuda(*aux_in) && aux_in->dim() == 2 && aux_in->size(0) == a.M && aux_in->size(1) == a.N && aux_in->stride(1) == 1, "gemm: bad aux_in");
+    a.aux_in = aux_in->data_ptr(); a.ld_aux = aux_in->stride(0);
+  }
+  if (aux_out.has_value()) {
+    need(is_bf16_cuda(*aux_out) && aux_out->dim() == 2 && aux_out->size(0) == a.M && aux_out->size(1) == a.N && aux_out->stride(1) == 1, "gemm: bad aux_out");
+    a.aux_out = aux_out->data_ptr(); a.ld_aux = aux_out->stride(0);
+  }
+  if (rng.has_value()) {
+    need(rng->is_cuda() && rng->scalar_type() == at::kLong && rng->numel() >= 2, "gemm: rng must be CUDA int64[2]");
+    a.rng = (const uint64_t*)rng->data_ptr<int64_t>();
+  }
+  need(epilogue != ZTB_EPI_DROPOUT_ADD || a.rng != nullptr, "gemm: dropout epilogue needs rng");
+  check(ztb_gemm(&a, num_sms(), stream()), "gemm");
+  return C;
+}
+
+// Fused (reduce-scatter +) AdamW over this rank's segments.  grad_ptrs: device addresses of every
+// peer's flat gradient buffer (first = local).  segs: uint8 CUDA tensor of packed ZtbSegment.
+void adamw_shard(at::Tensor& master, at::Tensor& m, at::Tensor& v, at::Tensor& flat_param, std::vector<int64_t> grad_ptrs,
+                 bool grad_is_fp32, const at::Tensor& segs, int64_t nseg, int64_t total_tiles, double lr, double beta1, double beta2,
+                 double eps, double wd, double clip, double grad_scale, int64_t step, int64_t wait_flags_ptr, int64_t wait_value) {
+  need(master.is_cuda() && master.scalar_type() == at::kFloat && m.scalar_type() == at::kFloat && v.scalar_type() == at::kFloat, "adamw_shard: fp32 state");
+  need(is_bf16_cuda(flat_param), "adamw_shard: bf16 flat_param");
+  need(segs.is_cuda() && segs.scalar_type() == at::kByte && segs.numel() >= (int64_t)(nseg * sizeof(ZtbSegment)), "adamw_shard: segs");
+  c10::cuda::CUDAGuard g(master.device());
+  std::vector<const void*> gp;
+  for (auto x : grad_ptrs) gp.push_back(reinterpret_cast<const void*>(x));
+  ZtbAdamArgs a;
+  a.lr = (float)lr; a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps; a.wd = (float)wd; a.clip = (float)clip;
+  a.grad_scale = (float)grad_scale;
+  a.bc1 = (float)(1.0 - std::pow(beta1, (double)step));
+  a.bc2 = (float)(1.0 - std::pow(beta2, (double)step));
+  check(ztb_adamw_shard(master.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), flat_param.data_ptr(), gp.data(), (int)gp.size(),
+                        grad_is_fp32, reinterpret_cast<const ZtbSegment*>(segs.data_ptr()), (int)nseg, total_tiles, a,
+                        reinterpret_cast<const int*>(wait_flags_ptr), (int)wait_value, num_sms(), stream()), "adamw_shard");
+}
+
+int64_t segment_struct_size() { return sizeof(ZtbSegment); }
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("layernorm_fwd", &layernorm_fwd);
+  m.def("layernorm_bwd", &layernorm_bwd);
+  m.def("dropout_add", &dropout_add);
+  m.def("embedding_fwd", &embedding_fwd);
+  m.def("embedding_bwd_", &embedding_bwd_);
+  m.def("gelu_fwd", &gelu_fwd);
+  m.def("gelu_bwd", &gelu_bwd);
+  m.def("ce_fwd", &ce_fwd);
+  m.def("ce_bwd_", &ce_bwd_);
+  m.def("gemm", &gemm, py::arg("A"), py::arg("B"), py::arg("C") = py::none(), py::arg("epilogue") = 0, py::arg("aux_in") = py::none(),
+        py::arg("aux_out") = py::none(), py::arg("p") = 0.0, py::arg("rng") = py::none(), py::arg("op_id") = 0,
+        py::arg("accumulate") = false, py::arg("a_mn") = false, py::arg("b_mn") = false);
+  m.def("adamw_shard", &adamw_shard);
+  m.def("segment_struct_size", &segment_struct_size);
+}

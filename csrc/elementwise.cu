@@ -1,0 +1,423 @@
+// Memory-bound sm_100a kernels: LayerNorm (bias-free) fwd/bwd, dropout+residual fwd/bwd,
+// embedding gather / scatter-add, GELU backward, cross-entropy fwd/bwd over bf16 logits.
+// All are single-pass over HBM with 16-byte vector accesses; row reductions stay in
+// registers + warp shuffles.  Reference semantics: SURVEY 2.4-A rows K2, K3, K9, K11.
+#include "common.cuh"
+#include "launchers.h"
+
+namespace ztb {
+
+// ============================================================== LayerNorm
+// One warp per row, the whole row in registers: D = 256 * NV elements, lane l owns
+// 16-byte vectors v*32 + l  (v < NV).  Stats in fp32.
+template <int NV>
+__global__ void __launch_bounds__(128) layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                            bf16* __restrict__ y, float* __restrict__ mean,
+                                                            float* __restrict__ rstd, int M, float eps) {
+  constexpr int D = NV * 256;
+  int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  int lane = threadIdx.x & 31;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * D);
+  float v[NV * 8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    uint4 u = ld_nc_v4(xr + i * 32 + lane);
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    v[i * 8 + 0] = a.x; v[i * 8 + 1] = a.y; v[i * 8 + 2] = b.x; v[i * 8 + 3] = b.y;
+    v[i * 8 + 4] = c.x; v[i * 8 + 5] = c.y; v[i * 8 + 6] = d.x; v[i * 8 + 7] = d.y;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[i * 8 + k];
+  }
+  float mu = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV * 8; ++k) { float d = v[k] - mu; q += d * d; }
+  float rs = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+  if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    uint4 g = ld_v4(wr + i * 32 + lane);
+    float2 g0 = unpack_bf16(g.x), g1 = unpack_bf16(g.y), g2 = unpack_bf16(g.z), g3 = unpack_bf16(g.w);
+    uint4 o;
+    o.x = pack_bf16((v[i * 8 + 0] - mu) * rs * g0.x, (v[i * 8 + 1] - mu) * rs * g0.y);
+    o.y = pack_bf16((v[i * 8 + 2] - mu) * rs * g1.x, (v[i * 8 + 3] - mu) * rs * g1.y);
+    o.z = pack_bf16((v[i * 8 + 4] - mu) * rs * g2.x, (v[i * 8 + 5] - mu) * rs * g2.y);
+    o.w = pack_bf16((v[i * 8 + 6] - mu) * rs * g3.x, (v[i * 8 + 7] - mu) * rs * g3.y);
+    st_v4(yr + i * 32 + lane, o);
+  }
+}
+
+// Backward: dx = rstd * (dy*w - mean(dy*w) - xhat * mean(dy*w*xhat));  dw += sum_rows dy*xhat.
+// Persistent grid: each warp strides over rows and keeps its dw partial in registers; one
+// smem reduction + fp32 atomics per block at the end.
+template <int NV>
+__global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                            const bf16* __restrict__ w, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, bf16* __restrict__ dx,
+                                                            float* __restrict__ dw, int M) {
+  constexpr int D = NV * 256;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[NV * 8];
+#pragma unroll
+  for (int k = 0; k < NV * 8; ++k) acc[k] = 0.f;
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  for (int row = blockIdx.x * 4 + warp; row < M; row += gridDim.x * 4) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * D);
+    const uint4* gr = reinterpret_cast<const uint4*>(dy + (size_t)row * D);
+    float mu = mean[row], rs = rstd[row];
+    uint4 px[NV], pg[NV];  // packed bf16 copies kept for the second pass (registers: 8*NV)
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      px[i] = ld_nc_v4(xr + i * 32 + lane);
+      pg[i] = ld_nc_v4(gr + i * 32 + lane);
+      uint4 uw = ld_v4(wr + i * 32 + lane);
+      uint32_t xs[4] = {px[i].x, px[i].y, px[i].z, px[i].w}, gs[4] = {pg[i].x, pg[i].y, pg[i].z, pg[i].w};
+      uint32_t ws[4] = {uw.x, uw.y, uw.z, uw.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 xf = unpack_bf16(xs[k]), gf = unpack_bf16(gs[k]), wf = unpack_bf16(ws[k]);
+        int j = i * 8 + 2 * k;
+        float xh0 = (xf.x - mu) * rs, xh1 = (xf.y - mu) * rs;
+        acc[j] += gf.x * xh0; acc[j + 1] += gf.y * xh1;
+        float gw0 = gf.x * wf.x, gw1 = gf.y * wf.y;
+        s1 += gw0 + gw1;
+        s2 += gw0 * xh0 + gw1 * xh1;
+      }
+    }
+    s1 = warp_sum(s1) * (1.f / D);
+    s2 = warp_sum(s2) * (1.f / D);
+    uint4* dr = reinterpret_cast<uint4*>(dx + (size_t)row * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      uint4 uw = ld_v4(wr + i * 32 + lane);
+      uint32_t xs[4] = {px[i].x, px[i].y, px[i].z, px[i].w}, gs[4] = {pg[i].x, pg[i].y, pg[i].z, pg[i].w};
+      uint32_t ws[4] = {uw.x, uw.y, uw.z, uw.w}, os[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 xf = unpack_bf16(xs[k]), gf = unpack_bf16(gs[k]), wf = unpack_bf16(ws[k]);
+        float xh0 = (xf.x - mu) * rs, xh1 = (xf.y - mu) * rs;
+        os[k] = pack_bf16(rs * (gf.x * wf.x - s1 - xh0 * s2), rs * (gf.y * wf.y - s1 - xh1 * s2));
+      }
+      st_v4(dr + i * 32 + lane, make_uint4(os[0], os[1], os[2], os[3]));
+    }
+  }
+  __shared__ float red[4][NV * 256];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[warp][(i * 32 + lane) * 8 + k] = acc[i * 8 + k];
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += 128) atomicAdd(dw + c, red[0][c] + red[1][c] + red[2][c] + red[3][c]);
+}
+
+// Generic-D fallback (D not a multiple of 256, e.g. the 64-wide test model): one block per row.
+__global__ void layernorm_fwd_generic(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                                      float* __restrict__ mean, float* __restrict__ rstd, int M, int D, float eps) {
+  __shared__ float sh[2][4];
+  int row = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bf16* xr = x + (size_t)row * D;
+  float s = 0.f, q = 0.f;
+  for (int c = threadIdx.x; c < D; c += 128) { float v = __bfloat162float(xr[c]); s += v; q += v * v; }
+  s = warp_sum(s); q = warp_sum(q);
+  if (lane == 0) { sh[0][warp] = s; sh[1][warp] = q; }
+  __syncthreads();
+  s = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3];
+  q = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
+  float mu = s / D, rs = rsqrtf(fmaxf(q / D - mu * mu, 0.f) + eps);
+  if (threadIdx.x == 0) { mean[row] = mu; rstd[row] = rs; }
+  for (int c = threadIdx.x; c < D; c += 128)
+    y[(size_t)row * D + c] = __float2bfloat16((__bfloat162float(xr[c]) - mu) * rs * __bfloat162float(w[c]));
+}
+__global__ void layernorm_bwd_generic(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                      bf16* __restrict__ dx, float* __restrict__ dw, int M, int D) {
+  __shared__ float sh[2][4];
+  int row = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float mu = mean[row], rs = rstd[row], s1 = 0.f, s2 = 0.f;
+  for (int c = threadIdx.x; c < D; c += 128) {
+    float xh = (__bfloat162float(x[(size_t)row * D + c]) - mu) * rs;
+    float g = __bfloat162float(dy[(size_t)row * D + c]);
+    float gw = g * __bfloat162float(w[c]);
+    s1 += gw; s2 += gw * xh;
+    atomicAdd(dw + c, g * xh);
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { sh[0][warp] = s1; sh[1][warp] = s2; }
+  __syncthreads();
+  s1 = (sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3]) / D;
+  s2 = (sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3]) / D;
+  for (int c = threadIdx.x; c < D; c += 128) {
+    float xh = (__bfloat162float(x[(size_t)row * D + c]) - mu) * rs;
+    float gw = __bfloat162float(dy[(size_t)row * D + c]) * __bfloat162float(w[c]);
+    dx[(size_t)row * D + c] = __float2bfloat16(rs * (gw - s1 - xh * s2));
+  }
+}
+
+// ============================================================== dropout + residual
+// fwd: out = res + keep(idx) * y / (1-p);  bwd: dy = keep(idx) * dout / (1-p)  (dres = dout).
+// idx = flat element index; Philox counter idx/4, component idx%4 -- the same mapping the
+// GEMM epilogue uses, so a fused forward and this backward agree on the mask.
+template <bool kHasRes>
+__global__ void __launch_bounds__(256) dropout_add_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res,
+                                                          bf16* __restrict__ out, size_t n8, float p, float inv_keep,
+                                                          const uint64_t* __restrict__ rng, uint32_t op_id) {
+  uint64_t seed = rng[0], stream = rng[1] * 65536ull + op_id;
+  Philox ph(seed);
+  uint32_t thr = dropout_threshold(p);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    uint4 uy = ld_nc_v4(reinterpret_cast<const uint4*>(y) + i);
+    uint4 r0 = ph(2 * i, stream), r1 = ph(2 * i + 1, stream);
+    uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    uint32_t ys[4] = {uy.x, uy.y, uy.z, uy.w};
+    uint32_t rs[4] = {0, 0, 0, 0};
+    if (kHasRes) { uint4 ur = ld_nc_v4(reinterpret_cast<const uint4*>(res) + i); rs[0] = ur.x; rs[1] = ur.y; rs[2] = ur.z; rs[3] = ur.w; }
+    uint32_t os[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 yf = unpack_bf16(ys[k]);
+      float2 rf = kHasRes ? unpack_bf16(rs[k]) : make_float2(0.f, 0.f);
+      float a = (rr[2 * k] >= thr) ? yf.x * inv_keep : 0.f;
+      float b = (rr[2 * k + 1] >= thr) ? yf.y * inv_keep : 0.f;
+      os[k] = pack_bf16(rf.x + a, rf.y + b);
+    }
+    st_v4(reinterpret_cast<uint4*>(out) + i, make_uint4(os[0], os[1], os[2], os[3]));
+  }
+}
+
+// ============================================================== embedding
+__global__ void __launch_bounds__(128) embedding_fwd_kernel(const int* __restrict__ idx, const bf16* __restrict__ wte,
+                                                            bf16* __restrict__ out, int M, int D8, int V) {
+  int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  int t = idx[row];
+  t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+  const uint4* src = reinterpret_cast<const uint4*>(wte) + (size_t)t * D8;
+  uint4* dst = reinterpret_cast<uint4*>(out) + (size_t)row * D8;
+  for (int c = threadIdx.x & 31; c < D8; c += 32) st_v4(dst + c, ld_v4(src + c));
+}
+// scatter-add into the (bf16 or fp32) gradient of the tied embedding: red.global.add on bf16x2
+template <typename G>
+__global__ void __launch_bounds__(128) embedding_bwd_kernel(const int* __restrict__ idx, const bf16* __restrict__ dout,
+                                                            G* __restrict__ dwte, int M, int D, int V) {
+  int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  int t = idx[row];
+  if (t < 0 || t >= V) return;
+  const bf162* src = reinterpret_cast<const bf162*>(dout + (size_t)row * D);
+  for (int c = threadIdx.x & 31; c < D / 2; c += 32) {
+    bf162 v = src[c];
+    if constexpr (sizeof(G) == 2) {
+      atomicAdd(reinterpret_cast<bf162*>(dwte + (size_t)t * D) + c, v);
+    } else {
+      float2 f = __bfloat1622float2(v);
+      atomicAdd(reinterpret_cast<float*>(dwte + (size_t)t * D) + 2 * c, f.x);
+      atomicAdd(reinterpret_cast<float*>(dwte + (size_t)t * D) + 2 * c + 1, f.y);
+    }
+  }
+}
+
+// ============================================================== GELU backward
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const bf16* __restrict__ dg, const bf16* __restrict__ z,
+                                                       bf16* __restrict__ dz, size_t n8) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    uint4 a = ld_nc_v4(reinterpret_cast<const uint4*>(dg) + i), b = ld_nc_v4(reinterpret_cast<const uint4*>(z) + i);
+    uint32_t as[4] = {a.x, a.y, a.z, a.w}, bs[4] = {b.x, b.y, b.z, b.w}, os[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 g = unpack_bf16(as[k]), zz = unpack_bf16(bs[k]);
+      os[k] = pack_bf16(g.x * gelu_tanh_grad(zz.x), g.y * gelu_tanh_grad(zz.y));
+    }
+    st_v4(reinterpret_cast<uint4*>(dz) + i, make_uint4(os[0], os[1], os[2], os[3]));
+  }
+}
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const bf16* __restrict__ z, bf16* __restrict__ g, size_t n8) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    uint4 b = ld_nc_v4(reinterpret_cast<const uint4*>(z) + i);
+    uint32_t bs[4] = {b.x, b.y, b.z, b.w}, os[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 zz = unpack_bf16(bs[k]);
+      os[k] = pack_bf16(gelu_tanh(zz.x), gelu_tanh(zz.y));
+    }
+    st_v4(reinterpret_cast<uint4*>(g) + i, make_uint4(os[0], os[1], os[2], os[3]));
+  }
+}
+
+// ============================================================== cross entropy
+// fwd: one block per row, online (max, sum-exp) in a single pass over the bf16 logits.
+// Writes lse[row] and nll[row] = lse - logit[label] (0 when label < 0 = ignored row).
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const bf16* __restrict__ logits, const int* __restrict__ labels,
+                                                     float* __restrict__ lse, float* __restrict__ nll, int V, size_t ld) {
+  __shared__ float shm[8], shs[8];
+  int row = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bf16* lr = logits + (size_t)row * ld;
+  float mx = -INFINITY, sm = 0.f;
+  int V8 = V / 8;
+  const float L2E = 1.4426950408889634f;
+  for (int i = threadIdx.x; i < V8; i += 256) {
+    uint4 u = ld_nc_v4(reinterpret_cast<const uint4*>(lr) + i);
+    uint32_t us[4] = {u.x, u.y, u.z, u.w};
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { float2 t = unpack_bf16(us[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+    float m2 = f[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) m2 = fmaxf(m2, f[k]);
+    if (m2 > mx) { sm *= exp2f((mx - m2) * L2E); mx = m2; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm += exp2f((f[k] - mx) * L2E);
+  }
+  for (int c = V8 * 8 + threadIdx.x; c < V; c += 256) {
+    float f = __bfloat162float(lr[c]);
+    if (f > mx) { sm *= exp2f((mx - f) * L2E); mx = f; }
+    sm += exp2f((f - mx) * L2E);
+  }
+  float wm = warp_max(mx);
+  sm *= (mx == -INFINITY) ? 0.f : exp2f((mx - wm) * L2E);
+  sm = warp_sum(sm);
+  if (lane == 0) { shm[warp] = wm; shs[warp] = sm; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float M = shm[0];
+    for (int k = 1; k < 8; ++k) M = fmaxf(M, shm[k]);
+    float S = 0.f;
+    for (int k = 0; k < 8; ++k) S += shs[k] * exp2f((shm[k] - M) * L2E);
+    float l = M + logf(S);
+    lse[row] = l;
+    int lab = labels[row];
+    nll[row] = (lab >= 0 && lab < V) ? l - __bfloat162float(lr[lab]) : 0.f;
+  }
+}
+// bwd (in place): logits <- (softmax - onehot) * gscale[0] * inv_count ; ignored rows -> 0.
+__global__ void __launch_bounds__(256) ce_bwd_kernel(bf16* __restrict__ logits, const int* __restrict__ labels,
+                                                     const float* __restrict__ lse, const float* __restrict__ gscale,
+                                                     float inv_count, int V, size_t ld) {
+  int row = blockIdx.x;
+  bf16* lr = logits + (size_t)row * ld;
+  int lab = labels[row];
+  float l = lse[row];
+  float g = (lab >= 0 && lab < V) ? gscale[0] * inv_count : 0.f;
+  const float L2E = 1.4426950408889634f;
+  int V8 = V / 8;
+  for (int i = threadIdx.x; i < V8; i += 256) {
+    uint4 u = ld_v4(reinterpret_cast<const uint4*>(lr) + i);
+    uint32_t us[4] = {u.x, u.y, u.z, u.w}, os[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 t = unpack_bf16(us[k]);
+      int c = i * 8 + 2 * k;
+      float a = exp2f((t.x - l) * L2E) - (c == lab ? 1.f : 0.f);
+      float b = exp2f((t.y - l) * L2E) - (c + 1 == lab ? 1.f : 0.f);
+      os[k] = pack_bf16(a * g, b * g);
+    }
+    st_v4(reinterpret_cast<uint4*>(lr) + i, make_uint4(os[0], os[1], os[2], os[3]));
+  }
+  for (int c = V8 * 8 + threadIdx.x; c < V; c += 256) {
+    float t = __bfloat162float(lr[c]);
+    lr[c] = __float2bfloat16((exp2f((t - l) * L2E) - (c == lab ? 1.f : 0.f)) * g);
+  }
+}
+
+}  // namespace ztb
+
+using namespace ztb;
+
+static int grid_for(size_t n, int block, int max_blocks) {
+  size_t g = (n + block - 1) / block;
+  return (int)(g < (size_t)max_blocks ? (g ? g : 1) : max_blocks);
+}
+
+#define LN_DISPATCH(NV, KERNEL, GRID, ...)                                                     \
+  switch (NV) {                                                                                \
+    case 1: KERNEL<1><<<GRID, 128, 0, st>>>(__VA_ARGS__); break;                               \
+    case 2: KERNEL<2><<<GRID, 128, 0, st>>>(__VA_ARGS__); break;                               \
+    case 3: KERNEL<3><<<GRID, 128, 0, st>>>(__VA_ARGS__); break;                               \
+    case 4: KERNEL<4><<<GRID, 128, 0, st>>>(__VA_ARGS__); break;                               \
+    case 6: KERNEL<6><<<GRID, 128, 0, st>>>(__VA_ARGS__); break;                               \
+    case 8: KERNEL<8><<<GRID, 128, 0, st>>>(__VA_ARGS__); break;                               \
+  }
+
+static bool ln_fast(int D) {
+  int nv = D / 256;
+  return D % 256 == 0 && (nv == 1 || nv == 2 || nv == 3 || nv == 4 || nv == 6 || nv == 8);
+}
+
+int ztb_layernorm_fwd(const void* x, const void* w, void* y, float* mean, float* rstd, int M, int D, float eps, cudaStream_t st) {
+  if (ln_fast(D)) {
+    int nv = D / 256, grid = (M + 3) / 4;
+    LN_DISPATCH(nv, layernorm_fwd_kernel, grid, (const bf16*)x, (const bf16*)w, (bf16*)y, mean, rstd, M, eps)
+  } else {
+    layernorm_fwd_generic<<<M, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)y, mean, rstd, M, D, eps);
+  }
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int ztb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
+                      float* dw, int M, int D, int sms, cudaStream_t st) {
+  ZTB_CUDA_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * D, st));
+  if (ln_fast(D)) {
+    int nv = D / 256, grid = grid_for((M + 3) / 4, 1, sms * 4);
+    LN_DISPATCH(nv, layernorm_bwd_kernel, grid, (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M)
+  } else {
+    layernorm_bwd_generic<<<M, 128, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, D);
+  }
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int ztb_dropout_add(const void* y, const void* res, void* out, size_t n, float p, const uint64_t* rng, uint32_t op_id,
+                    int sms, cudaStream_t st) {
+  if (n % 8) { ztb_set_error("dropout_add", "numel must be a multiple of 8", __FILE__, __LINE__); return -1; }
+  size_t n8 = n / 8;
+  int grid = grid_for(n8, 256, sms * 8);
+  float inv_keep = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  if (res)
+    dropout_add_kernel<true><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)res, (bf16*)out, n8, p, inv_keep, rng, op_id);
+  else
+    dropout_add_kernel<false><<<grid, 256, 0, st>>>((const bf16*)y, nullptr, (bf16*)out, n8, p, inv_keep, rng, op_id);
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int ztb_embedding_fwd(const int* idx, const void* wte, void* out, int M, int D, int V, cudaStream_t st) {
+  embedding_fwd_kernel<<<(M + 3) / 4, 128, 0, st>>>(idx, (const bf16*)wte, (bf16*)out, M, D / 8, V);
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int ztb_embedding_bwd(const int* idx, const void* dout, void* dwte, int grad_is_fp32, int M, int D, int V, cudaStream_t st) {
+  if (grad_is_fp32)
+    embedding_bwd_kernel<float><<<(M + 3) / 4, 128, 0, st>>>(idx, (const bf16*)dout, (float*)dwte, M, D, V);
+  else
+    embedding_bwd_kernel<bf16><<<(M + 3) / 4, 128, 0, st>>>(idx, (const bf16*)dout, (bf16*)dwte, M, D, V);
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int ztb_gelu_bwd(const void* dg, const void* z, void* dz, size_t n, int sms, cudaStream_t st) {
+  gelu_bwd_kernel<<<grid_for(n / 8, 256, sms * 8), 256, 0, st>>>((const bf16*)dg, (const bf16*)z, (bf16*)dz, n / 8);
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int ztb_gelu_fwd(const void* z, void* g, size_t n, int sms, cudaStream_t st) {
+  gelu_fwd_kernel<<<grid_for(n / 8, 256, sms * 8), 256, 0, st>>>((const bf16*)z, (bf16*)g, n / 8);
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int ztb_ce_fwd(const void* logits, const int* labels, float* lse, float* nll, int M, int V, size_t ld, cudaStream_t st) {
+  ce_fwd_kernel<<<M, 256, 0, st>>>((const bf16*)logits, labels, lse, nll, V, ld);
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int ztb_ce_bwd(void* logits, const int* labels, const float* lse, const float* gscale, float inv_count, int M, int V,
+               size_t ld, cudaStream_t st) {
+  ce_bwd_kernel<<<M, 256, 0, st>>>((bf16*)logits, labels, lse, gscale, inv_count, V, ld);
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

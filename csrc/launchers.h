@@ -1,0 +1,58 @@
+// C launcher prototypes shared by the .cu translation units and bindings.cpp.
+// Every launcher returns 0 on success (or a cudaError_t / -1, message in ztb_last_error()).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+void ztb_set_error(const char* expr, const char* msg, const char* file, int line);
+const char* ztb_last_error();
+
+// ---- elementwise.cu
+int ztb_layernorm_fwd(const void* x, const void* w, void* y, float* mean, float* rstd, int M, int D, float eps, cudaStream_t st);
+int ztb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
+                      float* dw, int M, int D, int sms, cudaStream_t st);
+int ztb_dropout_add(const void* y, const void* res, void* out, size_t n, float p, const uint64_t* rng, uint32_t op_id,
+                    int sms, cudaStream_t st);
+int ztb_embedding_fwd(const int* idx, const void* wte, void* out, int M, int D, int V, cudaStream_t st);
+int ztb_embedding_bwd(const int* idx, const void* dout, void* dwte, int grad_is_fp32, int M, int D, int V, cudaStream_t st);
+int ztb_gelu_bwd(const void* dg, const void* z, void* dz, size_t n, int sms, cudaStream_t st);
+int ztb_gelu_fwd(const void* z, void* g, size_t n, int sms, cudaStream_t st);
+int ztb_ce_fwd(const void* logits, const int* labels, float* lse, float* nll, int M, int V, size_t ld, cudaStream_t st);
+int ztb_ce_bwd(void* logits, const int* labels, const float* lse, const float* gscale, float inv_count, int M, int V,
+               size_t ld, cudaStream_t st);
+
+// ---- optim.cu
+struct ZtbSegment {      // one parameter region's chunk owned by this rank
+  long long flat_off;    // element offset of the chunk in the flat param/grad buffers
+  long long shard_off;   // element offset in the rank's fp32 master/m/v shard
+  long long len;         // elements in the chunk
+  long long tile_begin;  // exclusive prefix sum of tiles over segments
+  int decay;             // weight decay applies
+  int pad;
+};
+struct ZtbAdamArgs {
+  float lr, beta1, beta2, eps, wd, clip, grad_scale, bc1, bc2;
+};
+// grads[p] = flat grad buffer of peer p (p = 0 is local); n_peers == 1 -> plain fused AdamW.
+int ztb_adamw_shard(float* master, float* m, float* v, void* flat_param, const void* const* grads, int n_peers,
+                    int grad_is_fp32, const ZtbSegment* segs, int nseg, long long total_tiles, ZtbAdamArgs a,
+                    const int* wait_flags, int wait_value, int sms, cudaStream_t st);
+
+// ---- gemm_tcgen05.cu
+enum ZtbEpilogue { ZTB_EPI_NONE = 0, ZTB_EPI_GELU = 1, ZTB_EPI_DROPOUT_ADD = 2, ZTB_EPI_GELU_BWD = 3 };
+struct ZtbGemmArgs {
+  const void* A; const void* B; void* C;   // C[M,N] = A[M,K] * B[N,K]^T  (bf16, K contiguous in both)
+  int M, N, K;
+  long long lda, ldb, ldc;                  // row strides in elements
+  int epilogue;
+  void* aux_out;                            // GELU: pre-activation Z[M,N] (optional)
+  const void* aux_in;                       // DROPOUT_ADD: residual[M,N]; GELU_BWD: Z[M,N]
+  long long ld_aux;
+  float p;                                  // dropout probability
+  const uint64_t* rng; uint32_t op_id;
+  int accumulate;                           // C += result (fp32 C when c_is_fp32)
+  int c_is_fp32;
+  int a_mn_major, b_mn_major;               // operand stored with M (resp. N) contiguous: A[K,M] / B[K,N]
+};
+int ztb_gemm(const ZtbGemmArgs* args, int sms, cudaStream_t st);

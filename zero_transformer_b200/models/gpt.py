@@ -94,8 +94,7 @@ class MLPBlock(nn.Module):
         self.gelu = cfg.gelu
 
     def forward(self, x, residual, train: bool):
-        h = ops.linear_gelu(x, self.fc_in.weight, self.gelu)
-        return ops.linear_dropout_add(h, self.fc_out.weight, residual, self.p, train)
+        return ops.mlp(x, self.fc_in.weight, self.fc_out.weight, residual, self.p, train, self.gelu)
 
 
 class CausalAttention(nn.Module):
@@ -168,6 +167,8 @@ class Transformer(nn.Module):
         return self.cfg.block_size
 
     def hidden(self, x: torch.Tensor, train: bool = False, past_states=None, use_cache: bool = False):
+        if train:
+            ops.begin_forward(self.wte.weight.device)
         h = ops.embedding(x, self.wte.weight)
         presents = []
         for i, blk in enumerate(self.blocks):

@@ -58,6 +58,21 @@ def linear_dropout_add(x, w, residual, p: float, training: bool):
     return reference.linear_dropout_add(x, w, residual, p, training)
 
 
+def mlp(x, w1, w2, residual, p: float, training: bool, approximate: str = "tanh"):
+    """``residual + dropout(gelu(x @ w1.T) @ w2.T)`` (reference MLPBlock, ``layers.py:47-77``)."""
+    if _use_cuda(x) and approximate == "tanh":
+        return _k().mlp(x, w1, w2, residual, p, training)
+    return reference.linear_dropout_add(reference.linear_gelu(x, w1, approximate), w2, residual, p, training)
+
+
+def begin_forward(device) -> None:
+    """Start a new dropout stream (one per training forward / micro-step)."""
+    import torch as _t
+
+    if _t.device(device).type == "cuda" and not _FORCE_REF:
+        _k().begin_forward(device)
+
+
 def dropout_add(y, residual, p: float, training: bool):
     if _use_cuda(y):
         return _k().dropout_add(y, residual, p, training)

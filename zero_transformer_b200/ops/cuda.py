@@ -1,0 +1,402 @@
+"""CUDA op layer: ``torch.autograd.Function`` wrappers around the hand-written
+sm_100a kernels in ``csrc/`` (loaded from ``zero_transformer_b200/_ext``).
+
+Importing this module on a box where the extension is not built raises -- there
+is no silent eager fallback on the product path.  Library GEMMs (cuBLAS through
+``torch.matmul``) are used only for shapes the tcgen05 kernel does not cover
+(tiny/odd problem sizes such as the 64-wide test model or 1-token decode).
+
+Fusions implemented here:
+  K6/K8+K9  projection GEMM with dropout+residual epilogue (Philox mask regenerated in backward)
+  K7        fc_in GEMM with tanh-GELU epilogue that also emits the pre-activation
+  K7 bwd    fc_out dgrad GEMM with GELU-backward epilogue (dZ = (dY W2) * gelu'(Z))
+  K12       wgrad GEMMs accumulate straight into the flat gradient buffer (beta = 1, no
+            separate .grad add) when the parameter already has a ``.grad`` buffer
+  K10+K11   LM head GEMM -> single-pass CE; dlogits overwrite the logits in place
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from . import reference
+from ._build import load
+
+_C = load()
+
+EPI_NONE, EPI_GELU, EPI_DROPOUT_ADD, EPI_GELU_BWD = 0, 1, 2, 3
+
+
+class _Config:
+    # escape hatches for bring-up / A-B measurements (the defaults are the product path)
+    tc_gemm = os.environ.get("ZTB_TC_GEMM", "1") == "1"          # tcgen05 GEMM (0 -> cuBLAS everywhere)
+    tc_gemm_bwd = os.environ.get("ZTB_TC_GEMM_BWD", "1") == "1"  # MN-major dgrad/wgrad on tcgen05
+    fuse_wgrad = os.environ.get("ZTB_FUSE_WGRAD", "1") == "1"    # accumulate dW into param.grad in the epilogue
+    attn_impl = os.environ.get("ZTB_ATTN", "auto")                # auto | tc (own kernel) | flash (flash_attn library) | ref
+
+
+CONFIG = _Config()
+
+# ---------------------------------------------------------------------------
+# Dropout RNG: one device-resident (seed, offset) pair per device so the whole
+# step is CUDA-graph capturable.  Each dropout site of a forward pass gets a
+# distinct op_id; the offset advances once per forward (= micro-step).
+# ---------------------------------------------------------------------------
+_rng = {}
+_op_counter = [0]
+
+
+def rng_state(device) -> torch.Tensor:
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _rng:
+        _rng[key] = torch.tensor([0x5EED5EED, 0], dtype=torch.int64, device=device)
+    return _rng[key]
+
+
+def manual_seed(seed: int, device=None) -> None:
+    st = rng_state(device or torch.device("cuda", torch.cuda.current_device()))
+    st.copy_(torch.tensor([seed, 0], dtype=torch.int64))
+
+
+def begin_forward(device) -> None:
+    """Call once per training forward: new dropout stream, op ids restart at 0."""
+    rng_state(device)[1:2].add_(1)
+    _op_counter[0] = 0
+
+
+def _next_op_id() -> int:
+    _op_counter[0] += 1
+    return _op_counter[0]
+
+
+# ---------------------------------------------------------------------------
+# GEMM front-end
+# ---------------------------------------------------------------------------
+def _tc_ok(M: int, N: int, K: int) -> bool:
+    return CONFIG.tc_gemm and M >= 128 and N >= 256 and K >= 64 and N % 8 == 0 and K % 8 == 0
+
+
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, **kw) -> torch.Tensor:
+    """``a[M,K] @ b[N,K].T`` on the tcgen05 kernel."""
+    return _C.gemm(a, b, **kw)
+
+
+def _mm_fwd(x2: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    M, K = x2.shape
+    if _tc_ok(M, w.shape[0], K):
+        return _C.gemm(x2, w)
+    return x2 @ w.t()
+
+
+def _mm_dgrad(dy: torch.Tensor, w: torch.Tensor, **kw) -> torch.Tensor:
+    """dX[M,K] = dY[M,N] @ W[N,K]  (W consumed MN-major, no transpose copy)."""
+    M, N = dy.shape
+    K = w.shape[1]
+    if CONFIG.tc_gemm_bwd and _tc_ok(M, K, N) and M % 8 == 0:
+        return _C.gemm(dy, w, b_mn=True, **kw)
+    assert not kw, "fused dgrad epilogue needs the tcgen05 path"
+    return dy @ w
+
+
+def _mm_wgrad(dy: torch.Tensor, x2: torch.Tensor, w: torch.Tensor) -> Optional[torch.Tensor]:
+    """dW[N,K] = dY[M,N]^T @ X[M,K].  When ``w.grad`` already exists (the ZeRO-1 flat gradient
+    buffer) the product is accumulated into it inside the GEMM epilogue and ``None`` is returned."""
+    M, N = dy.shape
+    K = x2.shape[1]
+    tc = CONFIG.tc_gemm_bwd and _tc_ok(N, K, M) and N % 8 == 0
+    if CONFIG.fuse_wgrad and w.grad is not None and w.grad.is_contiguous():
+        if tc:
+            _C.gemm(dy, x2, C=w.grad, accumulate=True, a_mn=True, b_mn=True)
+        else:
+            w.grad.addmm_(dy.t(), x2) if w.grad.dtype == dy.dtype else w.grad.add_((dy.t() @ x2).to(w.grad.dtype))
+        return None
+    if tc:
+        return _C.gemm(dy, x2, a_mn=True, b_mn=True)
+    return dy.t() @ x2
+
+
+def _dropout_bwd(dout2: torch.Tensor, p: float, training: bool, op_id: int, rng: torch.Tensor) -> torch.Tensor:
+    if not training or p <= 0.0:
+        return dout2
+    return _C.dropout_add(dout2, None, p, rng, op_id)
+
+
+# ---------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        xc = x.contiguous()
+        y, mean, rstd = _C.layernorm_fwd(xc, w.contiguous(), eps)
+        ctx.save_for_backward(xc, w, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        dx, dw = _C.layernorm_bwd(dy.contiguous(), x, w.contiguous(), mean, rstd)
+        return dx, dw.to(w.dtype), None
+
+
+def layernorm(x, weight, eps):
+    return _LayerNorm.apply(x, weight, eps)
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        x2 = x.reshape(-1, x.shape[-1])
+        ctx.save_for_backward(x2, w)
+        ctx.xshape = x.shape
+        return _mm_fwd(x2, w).view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = _mm_dgrad(dy2, w).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+        dw = _mm_wgrad(dy2, x2, w) if ctx.needs_input_grad[1] else None
+        return dx, dw
+
+
+def linear(x, w):
+    return _Linear.apply(x, w)
+
+
+class _LinearDropoutAdd(torch.autograd.Function):
+    """``residual + dropout(x @ w.T)`` in one GEMM (epilogue does mask + scale + add)."""
+
+    @staticmethod
+    def forward(ctx, x, w, residual, p, training):
+        x2 = x.reshape(-1, x.shape[-1])
+        r2 = residual.reshape(-1, residual.shape[-1])
+        M, K = x2.shape
+        N = w.shape[0]
+        pe = float(p) if training else 0.0
+        rng = rng_state(x.device)
+        op_id = _next_op_id() if pe > 0 else 0
+        if _tc_ok(M, N, K):
+            out = _C.gemm(x2, w, epilogue=EPI_DROPOUT_ADD, aux_in=r2, p=pe, rng=rng, op_id=op_id)
+        else:
+            y = x2 @ w.t()
+            out = _C.dropout_add(y, r2.contiguous(), pe, rng, op_id) if y.numel() % 8 == 0 else r2 + y
+        ctx.save_for_backward(x2, w)
+        ctx.meta = (x.shape, pe, op_id)
+        return out.view(residual.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, w = ctx.saved_tensors
+        xshape, pe, op_id = ctx.meta
+        d2 = dout.reshape(-1, dout.shape[-1])
+        if not d2.is_contiguous():
+            d2 = d2.contiguous()
+        dy = _dropout_bwd(d2, pe, pe > 0, op_id, rng_state(dout.device))
+        dx = _mm_dgrad(dy, w).view(xshape) if ctx.needs_input_grad[0] else None
+        dw = _mm_wgrad(dy, x2, w) if ctx.needs_input_grad[1] else None
+        return dx, dw, dout, None, None
+
+
+def linear_dropout_add(x, w, residual, p, training):
+    return _LinearDropoutAdd.apply(x, w, residual, p, training)
+
+
+class _MLP(torch.autograd.Function):
+    """``residual + dropout(gelu(x W1^T) W2^T)`` -- 2 GEMMs forward, 4 backward, every
+    elementwise op folded into a GEMM epilogue except the backward dropout mask."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, residual, p, training):
+        x2 = x.reshape(-1, x.shape[-1])
+        r2 = residual.reshape(-1, residual.shape[-1])
+        M, D = x2.shape
+        H = w1.shape[0]
+        pe = float(p) if training else 0.0
+        rng = rng_state(x.device)
+        op_id = _next_op_id() if pe > 0 else 0
+        if _tc_ok(M, H, D):
+            z = torch.empty(M, H, dtype=x2.dtype, device=x2.device)
+            g = _C.gemm(x2, w1, epilogue=EPI_GELU, aux_out=z)
+        else:
+            z = x2 @ w1.t()
+            g = _C.gelu_fwd(z) if z.numel() % 8 == 0 else torch.nn.functional.gelu(z, approximate="tanh")
+        if _tc_ok(M, D, H):
+            out = _C.gemm(g, w2, epilogue=EPI_DROPOUT_ADD, aux_in=r2, p=pe, rng=rng, op_id=op_id)
+        else:
+            y = g @ w2.t()
+            out = _C.dropout_add(y, r2.contiguous(), pe, rng, op_id) if y.numel() % 8 == 0 else r2 + y
+        ctx.save_for_backward(x2, w1, w2, z, g)
+        ctx.meta = (x.shape, pe, op_id)
+        return out.view(residual.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, w1, w2, z, g = ctx.saved_tensors
+        xshape, pe, op_id = ctx.meta
+        d2 = dout.reshape(-1, dout.shape[-1])
+        if not d2.is_contiguous():
+            d2 = d2.contiguous()
+        dy = _dropout_bwd(d2, pe, pe > 0, op_id, rng_state(dout.device))
+        M, D = dy.shape
+        H = w2.shape[1]
+        dw2 = _mm_wgrad(dy, g, w2)
+        if CONFIG.tc_gemm_bwd and _tc_ok(M, H, D):
+            dz = _C.gemm(dy, w2, epilogue=EPI_GELU_BWD, aux_in=z, b_mn=True)  # (dY W2) * gelu'(Z)
+        else:
+            dg = dy @ w2
+            dz = _C.gelu_bwd(dg.contiguous(), z) if z.numel() % 8 == 0 else dg * _gelu_grad_ref(z)
+        dw1 = _mm_wgrad(dz, x2, w1)
+        dx = _mm_dgrad(dz, w1).view(xshape)
+        return dx, dw1, dw2, dout, None, None
+
+
+def _gelu_grad_ref(z):
+    zf = z.float().requires_grad_(True)
+    with torch.enable_grad():
+        (g,) = torch.autograd.grad(torch.nn.functional.gelu(zf, approximate="tanh").sum(), zf)
+    return g.to(z.dtype)
+
+
+def mlp(x, w1, w2, residual, p, training):
+    return _MLP.apply(x, w1, w2, residual, p, training)
+
+
+class _LinearGelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        x2 = x.reshape(-1, x.shape[-1])
+        M, K = x2.shape
+        if _tc_ok(M, w.shape[0], K):
+            z = torch.empty(M, w.shape[0], dtype=x2.dtype, device=x2.device)
+            g = _C.gemm(x2, w, epilogue=EPI_GELU, aux_out=z)
+        else:
+            z = x2 @ w.t()
+            g = torch.nn.functional.gelu(z, approximate="tanh")
+        ctx.save_for_backward(x2, w, z)
+        ctx.xshape = x.shape
+        return g.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dg):
+        x2, w, z = ctx.saved_tensors
+        dg2 = dg.reshape(-1, dg.shape[-1]).contiguous()
+        dz = _C.gelu_bwd(dg2, z) if z.numel() % 8 == 0 else dg2 * _gelu_grad_ref(z)
+        return _mm_dgrad(dz, w).view(ctx.xshape), _mm_wgrad(dz, x2, w)
+
+
+def linear_gelu(x, w):
+    return _LinearGelu.apply(x, w)
+
+
+class _DropoutAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, residual, p, training):
+        pe = float(p) if training else 0.0
+        op_id = _next_op_id() if pe > 0 else 0
+        ctx.meta = (pe, op_id)
+        return _C.dropout_add(y.contiguous(), residual.contiguous(), pe, rng_state(y.device), op_id)
+
+    @staticmethod
+    def backward(ctx, dout):
+        pe, op_id = ctx.meta
+        return _dropout_bwd(dout.contiguous(), pe, pe > 0, op_id, rng_state(dout.device)), dout, None, None
+
+
+def dropout_add(y, residual, p, training):
+    if y.numel() % 8:
+        return reference.dropout_add(y, residual, p, training)
+    return _DropoutAdd.apply(y, residual, p, training)
+
+
+# ---------------------------------------------------------------------------
+class _Embedding(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, wte):
+        idx32 = idx.to(torch.int32).contiguous()
+        ctx.save_for_backward(idx32)
+        ctx.wte = wte
+        return _C.embedding_fwd(idx32, wte)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx32,) = ctx.saved_tensors
+        wte = ctx.wte
+        d = dout.contiguous()
+        if CONFIG.fuse_wgrad and wte.grad is not None and wte.grad.is_contiguous():
+            _C.embedding_bwd_(idx32, d, wte.grad)  # scatter-add into the shared (tied) gradient buffer
+            return None, None
+        dw = torch.zeros_like(wte)
+        _C.embedding_bwd_(idx32, d, dw)
+        return None, dw
+
+
+def embedding(idx, wte):
+    if wte.shape[1] % 8:
+        return reference.embedding(idx, wte)
+    return _Embedding.apply(idx, wte)
+
+
+# ---------------------------------------------------------------------------
+class _LMHeadLoss(torch.autograd.Function):
+    """Tied LM head + shifted cross entropy.  The bf16 logits are produced by the tcgen05 GEMM,
+    reduced to per-row log-sum-exp in one pass, and overwritten in place by dlogits in backward
+    (no fp32 logits, no one-hot, no softmax tensor; reference GPT.py:100-111 materialises all three)."""
+
+    @staticmethod
+    def forward(ctx, h, wte, tokens):
+        B, T, D = h.shape
+        h2 = h.reshape(B * T, D)
+        logits = _mm_fwd(h2, wte)  # (B*T, V) bf16
+        labels = torch.full((B, T), -1, dtype=torch.int32, device=h.device)
+        labels[:, :-1] = tokens[:, 1:].to(torch.int32)
+        labels = labels.view(-1)
+        lse, nll = _C.ce_fwd(logits, labels)
+        count = B * (T - 1)
+        ctx.save_for_backward(h2, wte, labels, lse)
+        ctx.logits = logits
+        ctx.meta = (h.shape, count)
+        return nll.sum() / count
+
+    @staticmethod
+    def backward(ctx, gout):
+        h2, wte, labels, lse = ctx.saved_tensors
+        hshape, count = ctx.meta
+        logits = ctx.logits
+        ctx.logits = None
+        _C.ce_bwd_(logits, labels, lse, gout.reshape(1).float().contiguous(), 1.0 / count)
+        dh = _mm_dgrad(logits, wte).view(hshape)
+        dw = _mm_wgrad(logits, h2, wte)
+        return dh, dw, None
+
+
+def lm_head_loss(h, wte, tokens):
+    if wte.shape[0] % 8 or h.dtype != torch.bfloat16:
+        return reference.lm_head_loss(h, wte, tokens)
+    return _LMHeadLoss.apply(h, wte, tokens)
+
+
+def cross_entropy(logits, labels):
+    # logits-returning API path (not on the training hot path): reference math on the GPU
+    return reference.cross_entropy(logits, labels)
+
+
+# ---------------------------------------------------------------------------
+def attention(qkv, slopes, n_head, scale, p, training):
+    impl = CONFIG.attn_impl
+    if impl in ("auto", "tc") and hasattr(_C, "attention_fwd"):
+        from .attention_cuda import alibi_attention
+
+        return alibi_attention(qkv, slopes, n_head, scale, p if training else 0.0)
+    if impl in ("auto", "flash"):
+        from flash_attn import flash_attn_qkvpacked_func
+
+        B, T, D3 = qkv.shape
+        hd = D3 // 3 // n_head
+        out = flash_attn_qkvpacked_func(qkv.view(B, T, 3, n_head, hd), dropout_p=p if training else 0.0, softmax_scale=scale,
+                                        causal=True, alibi_slopes=slopes.float() if slopes is not None else None)
+        return out.reshape(B, T, n_head * hd)
+    return reference.attention(qkv, slopes, n_head, scale, p, training)
