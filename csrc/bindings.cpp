@@ -181,6 +181,40 @@ void adamw_shard(at::Tensor& master, at::Tensor& m, at::Tensor& v, at::Tensor& f
 
 int64_t segment_struct_size() { return sizeof(ZtbSegment); }
 
+std::vector<void*> to_ptrs(const std::vector<int64_t>& v) {
+  std::vector<void*> o;
+  for (auto x : v) o.push_back(reinterpret_cast<void*>(x));
+  return o;
+}
+
+// release-store `value` into slot `slot` of every listed flag pad (device addresses, peers included)
+void signal(std::vector<int64_t> pad_ptrs, int64_t slot, int64_t value) {
+  auto p = to_ptrs(pad_ptrs);
+  check(ztb_signal(p.data(), (int)p.size(), (int)slot, (int)value, stream()), "signal");
+}
+
+void allgather_pull(at::Tensor& flat_param, std::vector<int64_t> src_ptrs, const at::Tensor& segs, int64_t nseg, int64_t total_tiles,
+                    int64_t flags_ptr, int64_t wait_value) {
+  need(is_bf16_cuda(flat_param), "allgather_pull: bf16 flat_param");
+  c10::cuda::CUDAGuard g(flat_param.device());
+  auto p = to_ptrs(src_ptrs);
+  check(ztb_allgather_pull(flat_param.data_ptr(), p.data(), (int)p.size(), reinterpret_cast<const ZtbSegment*>(segs.data_ptr()), (int)nseg,
+                           total_tiles, reinterpret_cast<const int*>(flags_ptr), (int)wait_value, num_sms(), stream()), "allgather_pull");
+}
+
+void reduce_scatter(at::Tensor& out, std::vector<int64_t> grad_ptrs, const at::Tensor& segs, int64_t nseg, int64_t total_tiles,
+                    int64_t flags_ptr, int64_t wait_value) {
+  need(is_bf16_cuda(out), "reduce_scatter: bf16 out");
+  c10::cuda::CUDAGuard g(out.device());
+  auto p = to_ptrs(grad_ptrs);
+  check(ztb_reduce_scatter(out.data_ptr(), p.data(), (int)p.size(), reinterpret_cast<const ZtbSegment*>(segs.data_ptr()), (int)nseg,
+                           total_tiles, reinterpret_cast<const int*>(flags_ptr), (int)wait_value, num_sms(), stream()), "reduce_scatter");
+}
+
+void p2p_copy(int64_t dst_ptr, int64_t src_ptr, int64_t bytes) {
+  check(ztb_p2p_copy(reinterpret_cast<void*>(dst_ptr), reinterpret_cast<const void*>(src_ptr), (size_t)bytes, num_sms(), stream()), "p2p_copy");
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -198,4 +232,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("accumulate") = false, py::arg("a_mn") = false, py::arg("b_mn") = false);
   m.def("adamw_shard", &adamw_shard);
   m.def("segment_struct_size", &segment_struct_size);
+  m.def("signal", &signal);
+  m.def("allgather_pull", &allgather_pull);
+  m.def("reduce_scatter", &reduce_scatter);
+  m.def("p2p_copy", &p2p_copy);
 }

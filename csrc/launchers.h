@@ -56,3 +56,11 @@ struct ZtbGemmArgs {
   int a_mn_major, b_mn_major;               // operand stored with M (resp. N) contiguous: A[K,M] / B[K,N]
 };
 int ztb_gemm(const ZtbGemmArgs* args, int sms, cudaStream_t st);
+
+// ---- comm.cu (NVLink peer-memory kernels; all pointers are device addresses, peers mapped via symmetric memory)
+int ztb_signal(void* const* pads, int n, int slot, int value, cudaStream_t st);
+int ztb_allgather_pull(void* dst, void* const* srcs, int world, const ZtbSegment* segs, int nseg, long long total_tiles,
+                       const int* flags, int wait_value, int sms, cudaStream_t st);
+int ztb_reduce_scatter(void* out, void* const* grads, int n_peers, const ZtbSegment* segs, int nseg, long long total_tiles,
+                       const int* flags, int wait_value, int sms, cudaStream_t st);
+int ztb_p2p_copy(void* dst, const void* src, size_t bytes, int sms, cudaStream_t st);

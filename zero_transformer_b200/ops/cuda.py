@@ -24,7 +24,39 @@ import torch
 from . import reference
 from ._build import load
 
-_C = load()
+
+
+class _LaunchCounter:
+    """Counts calls into the extension (each call launches one of our kernels; a few launch two)."""
+
+    def __init__(self):
+        self.count = 0
+
+    def reset(self):
+        self.count = 0
+
+
+LAUNCHES = _LaunchCounter()
+
+
+class _Counting:
+    def __init__(self, mod):
+        self._mod = mod
+
+    def __getattr__(self, name):
+        fn = getattr(self._mod, name)
+        if not callable(fn):
+            return fn
+
+        def wrapped(*a, **k):
+            LAUNCHES.count += 1
+            return fn(*a, **k)
+
+        setattr(self, name, wrapped)
+        return wrapped
+
+
+_C = _Counting(load())
 
 EPI_NONE, EPI_GELU, EPI_DROPOUT_ADD, EPI_GELU_BWD = 0, 1, 2, 3
 
@@ -387,7 +419,7 @@ def cross_entropy(logits, labels):
 # ---------------------------------------------------------------------------
 def attention(qkv, slopes, n_head, scale, p, training):
     impl = CONFIG.attn_impl
-    if impl in ("auto", "tc") and hasattr(_C, "attention_fwd"):
+    if impl in ("auto", "tc") and hasattr(_C._mod, "attention_fwd"):
         from .attention_cuda import alibi_attention
 
         return alibi_attention(qkv, slopes, n_head, scale, p if training else 0.0)

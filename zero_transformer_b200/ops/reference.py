@@ -93,6 +93,14 @@ def attention(
         k = torch.cat([kv_cache[0], k], dim=2)
         v = torch.cat([kv_cache[1], v], dim=2)
     Tk = k.shape[2]
+    if qkv.is_cuda and kv_cache is None:
+        # stock-PyTorch GPU path (baseline arm): SDPA with the ALiBi+causal additive mask
+        i = torch.arange(T, device=qkv.device).view(T, 1)
+        j = torch.arange(T, device=qkv.device).view(1, T)
+        bias = alibi_bias(slopes, T, T) if slopes is not None else torch.zeros(1, T, T, device=qkv.device)
+        bias = bias.masked_fill(j > i, float("-inf")).to(q.dtype).unsqueeze(0)
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, dropout_p=p if training else 0.0, scale=scale)
+        return o.transpose(1, 2).reshape(B, T, D)
     s = torch.matmul(q.float(), k.float().transpose(-1, -2)) * scale
     if slopes is not None:
         s = s + alibi_bias(slopes, T, Tk).unsqueeze(0)

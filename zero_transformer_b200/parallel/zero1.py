@@ -81,6 +81,10 @@ class Zero1Engine:
         src_dtype = named[0][1].dtype
         self.compute_dtype = compute_dtype or (torch.bfloat16 if dev.type == "cuda" else src_dtype)
         self.grad_dtype = grad_dtype or self.compute_dtype
+        if self.grad_dtype != self.compute_dtype:
+            # autograd requires param.grad to share the parameter's dtype; the reference accumulates
+            # bf16 gradients as well (xmap_train_functions.py:62)
+            raise ValueError("grad_dtype must equal compute_dtype (fp32 main-grads are not implemented)")
         if decay_mask is None:
             decay_mask = model.decay_mask() if hasattr(model, "decay_mask") else {n: p.ndim >= 2 for n, p in named}
         self.layout = FlatLayout([(n, tuple(p.shape)) for n, p in named], decay_mask, self.world, bucket_of)
