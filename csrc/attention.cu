@@ -1,2 +1,777 @@
-// placeholder translation unit until the tcgen05 attention kernel lands
+// ALiBi-biased causal flash attention on tcgen05 / TMEM (forward).
+//
+// Reference semantics (src/models/layers.py:145-178): S = Q K^T * scale + slope_h * (j - i), causal
+// mask, fp32 softmax, dropout on the probabilities, O = P V.  The reference materialises the
+// (b, h, T, T) fp32 score tensor; here nothing of size T^2 ever leaves the SM.
+//
+// One CTA per (batch, head, 128-query block); KV blocks of 128 keys are streamed through a
+// 2-stage TMA ring.  Warp roles: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one thread),
+// warps 2-5 = softmax (one query row per thread = one TMEM lane, so row max / row sum need no
+// shuffles).  Per KV block:
+//     S_j   = Q K_j^T            tcgen05.mma  SS  (both operands K-major)      -> TMEM (2 buffers)
+//     P_j   = exp2(S_j*c + alibi - m)  (registers; lazy rescale: m only moves when the row max
+//             grows by more than 2^8, FA4-style)                               -> smem bf16 (SW128)
+//     O    += P_j V_j            tcgen05.mma  SS  (V consumed MN-major)         -> TMEM
+// S_{j+1} is issued before P_j is consumed so the tensor core overlaps the softmax.  Dropout keeps
+// an element iff an 8-bit Philox lane >= round(256 p) (16 decisions per Philox call) and the
+// 1/(1-p') factor is folded into the final 1/l normalisation.
+#include <cuda.h>
+#include <stdio.h>
+
+#include "common.cuh"
 #include "launchers.h"
+
+namespace ztb {
+
+constexpr int ATT_BM = 128, ATT_BN = 128;
+constexpr int ATT_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (2 column halves x 4 lane quarters)
+
+ZTB_DEVINL float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int HD>
+struct AttnSmem {
+  static constexpr int CH = HD / 64;               // 64-column (128-byte) chunks per row
+  static constexpr int TILE = 128 * 128 * CH;      // bytes of a [128 x HD] bf16 tile
+  static constexpr int Q_OFF = 0;
+  static constexpr int K_OFF = TILE;               // 2 stages
+  static constexpr int V_OFF = 3 * TILE;           // 2 stages
+  static constexpr int P_OFF = 5 * TILE;           // [128 x 128] bf16 = 32 KB (also O staging)
+  static constexpr int BAR_OFF = 5 * TILE + 32768;
+  static constexpr int TOTAL = BAR_OFF + 128 + 3072 + 1024;  // barriers + row-max/row-sum exchange
+};
+
+struct AttnParams {
+  int B, T, H;
+  float scale_log2;          // softmax scale * log2(e)
+  const float* slopes;       // [H] or nullptr
+  float* lse;                // [B, H, T] natural-log LSE (for backward)
+  uint32_t drop_thr8;        // keep iff byte >= thr (0 = no dropout)
+  float inv_keep;            // 1 / (1 - thr/256)
+  const uint64_t* rng;
+  uint32_t op_id;
+};
+
+ZTB_DEVINL void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+// 16 keep/drop decisions for elements [16*g, 16*g+16) of row `row_id` from one Philox call
+ZTB_DEVINL uint4 attn_dropout_bits(const Philox& ph, uint64_t row_id, uint32_t g, uint64_t stream) {
+  return ph(row_id * 4096ull + g, stream);
+}
+
+template <int HD>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
+  using L = AttnSmem<HD>;
+  constexpr int CH = L::CH;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smQ = smem + L::Q_OFF;
+  uint8_t* smK = smem + L::K_OFF;
+  uint8_t* smV = smem + L::V_OFF;
+  uint8_t* smP = smem + L::P_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* k_full = bars + 1;      // 2
+  uint64_t* v_full = bars + 3;      // 2
+  uint64_t* kv_empty = bars + 5;    // 2
+  uint64_t* s_full = bars + 7;      // 2
+  uint64_t* s_empty = bars + 9;     // 2
+  uint64_t* p_ready = bars + 11;    // 1
+  uint64_t* pv_done = bars + 12;    // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = gridDim.x - 1 - blockIdx.x;  // heavy (long) rows first
+  const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  const int D = p.H * HD;
+  const int nblk = qb + 1;                    // causal: KV blocks 0..qb
+  const int row0 = b * p.T + qb * ATT_BM;     // first global row of this query block
+  const int colQ = h * HD, colK = D + h * HD, colV = 2 * D + h * HD;
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmQKV); prefetch_tmap(&tmO); }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1);
+                                  mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 256); }
+    mbar_init(p_ready, 256);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;          // 2 x 128 columns
+  const uint32_t tO = tmem_base + 256;    // HD columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, L::TILE);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) tma_load_2d(smQ + c * 16384, &tmQKV, q_full, colQ + c * 64, row0);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        const int krow = b * p.T + j * ATT_BN;
+        mbar_expect_tx(&k_full[st], L::TILE);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) tma_load_2d(smK + st * L::TILE + c * 16384, &tmQKV, &k_full[st], colK + c * 64, krow);
+        mbar_expect_tx(&v_full[st], L::TILE);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) tma_load_2d(smV + st * L::TILE + c * 16384, &tmQKV, &v_full[st], colV + c * 64, krow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, HD, 0, 1);
+      const uint32_t q_addr = smem_u32(smQ), p_addr = smem_u32(smP);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&k_full[st], (j >> 1) & 1);
+        mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t k_addr = smem_u32(smK + st * L::TILE);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+          umma_f16_ss(tS + st * 128, make_smem_desc(q_addr + off, 16, 1024, kSwizzle128B),
+                      make_smem_desc(k_addr + off, 16, 1024, kSwizzle128B), idesc_s, k != 0);
+        }
+        umma_commit(&s_full[st]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        if (j + 1 < nblk) issue_s(j + 1);
+        mbar_wait(p_ready, j & 1);
+        mbar_wait(&v_full[st], (j >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t v_addr = smem_u32(smV + st * L::TILE);
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; ++k) {
+          uint64_t da = make_smem_desc(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, kSwizzle128B);
+          uint64_t db = make_smem_desc(v_addr + k * 2048, 16384, 1024, kSwizzle128B);
+          umma_f16_ss(tO, da, db, idesc_o, (j | k) != 0);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    // ===================================================== softmax warps
+    // thread = (query row r = TMEM lane, column half hf): two warps share each lane quarter and
+    // split the 128 key columns, so every SMSP runs two softmax warps.
+    const int sw = warp - 2;
+    const int quarter = warp & 3;
+    const int hf = sw >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int qi = qb * ATT_BM + r;
+    const float slope2 = p.slopes ? p.slopes[h] * 1.4426950408889634f : 0.f;
+    const bool use_drop = p.drop_thr8 != 0;
+    uint64_t seed = 0, stream = 0;
+    if (use_drop) { seed = p.rng[0]; stream = p.rng[1] * 65536ull + p.op_id; }
+    Philox ph(seed);
+    const uint64_t row_id = (uint64_t)bh * p.T + qi;
+    float* xch = reinterpret_cast<float*>(smem + L::BAR_OFF + 128);  // [2 parity][2 half][128] row-max exchange
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      const int st = j & 1;
+      mbar_wait(&s_full[st], (j >> 1) & 1);
+      tc_fence_after_sync();
+      float s[64];
+      {
+        uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+        tmem_ld_32x32b_x32(tS + lane_addr + st * 128 + hf * 64, sr);
+        tmem_ld_32x32b_x32(tS + lane_addr + st * 128 + hf * 64 + 32, sr + 32);
+        tmem_wait_ld();
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&s_empty[st]);
+      const int kv0 = j * ATT_BN + hf * 64;
+      const float base = slope2 * (float)(kv0 - qi);
+      const int cmax = r - hf * 64;          // columns > cmax are in the future (diagonal block only)
+      const bool diag = (j == qb);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        float v = fmaf(s[c], p.scale_log2, fmaf(slope2, (float)c, base));
+        if (diag && c > cmax) v = -INFINITY;
+        s[c] = v;
+        mx = fmaxf(mx, v);
+      }
+      xch[(j & 1) * 256 + hf * 128 + r] = mx;
+      named_bar_sync(3, 256);
+      mx = fmaxf(mx, xch[(j & 1) * 256 + (hf ^ 1) * 128 + r]);
+      float alpha = 1.f;
+      if (mx > m + 8.f) { alpha = ex2_ftz(m - mx); m = mx; }  // lazy rescale; first block: alpha = 0
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) { s[c] = ex2_ftz(s[c] - m); sum += s[c]; }
+      l = l * alpha + sum;
+      uint32_t pk[32];
+      if (use_drop) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 rb = attn_dropout_bits(ph, row_id, (uint32_t)(j * 8 + hf * 4 + g), stream);
+          uint32_t w[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            uint32_t b0 = (w[e >> 2] >> ((e & 3) * 8)) & 0xFF, b1 = (w[(e + 1) >> 2] >> (((e + 1) & 3) * 8)) & 0xFF;
+            float a0 = b0 >= p.drop_thr8 ? s[g * 16 + e] : 0.f, a1 = b1 >= p.drop_thr8 ? s[g * 16 + e + 1] : 0.f;
+            pk[g * 8 + (e >> 1)] = pack_bf16(a0, a1);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) pk[c] = pack_bf16(s[2 * c], s[2 * c + 1]);
+      }
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after_sync();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {  // this thread rescales its half of the O columns
+#pragma unroll
+          for (int c = 0; c < HD / 64; ++c) {
+            uint32_t o[32];
+            const uint32_t ta = tO + lane_addr + hf * (HD / 2) + c * 32;
+            tmem_ld_32x32b_x32(ta, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+            tmem_st_32x32b_x32(ta, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      uint8_t* prow = smP + hf * 16384 + r * 128;
+#pragma unroll
+      for (int c16 = 0; c16 < 8; ++c16)
+        *reinterpret_cast<uint4*>(prow + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[c16 * 4], pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]);
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(p_ready);
+    }
+    // ---- epilogue: combine the two partial row sums, O / l -> bf16 -> staging (P region) -> TMA store
+    xch[512 + hf * 128 + r] = l;
+    mbar_wait(pv_done, (nblk - 1) & 1);
+    tc_fence_after_sync();
+    named_bar_sync(3, 256);
+    l += xch[512 + (hf ^ 1) * 128 + r];
+    const float inv = (use_drop ? p.inv_keep : 1.f) / l;
+    constexpr int OC = HD / 2;               // O columns per thread
+#pragma unroll
+    for (int c = 0; c < OC / 32; ++c) {
+      uint32_t o[32];
+      const int col = hf * OC + c * 32;      // first O column of this chunk
+      tmem_ld_32x32b_x32(tO + lane_addr + col, o);
+      tmem_wait_ld();
+      uint8_t* orow = smP + (col >> 6) * 16384 + r * 128;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint4 o4 = make_uint4(pack_bf16(__uint_as_float(o[q4 * 8 + 0]) * inv, __uint_as_float(o[q4 * 8 + 1]) * inv),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 2]) * inv, __uint_as_float(o[q4 * 8 + 3]) * inv),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 4]) * inv, __uint_as_float(o[q4 * 8 + 5]) * inv),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 6]) * inv, __uint_as_float(o[q4 * 8 + 7]) * inv));
+        *reinterpret_cast<uint4*>(orow + (((((col & 63) >> 3) + q4) ^ (r & 7)) << 4)) = o4;
+      }
+    }
+    if (hf == 0) p.lse[(size_t)bh * p.T + qi] = (m + log2f(l)) * 0.6931471805599453f;
+    fence_proxy_async_smem();
+    named_bar_sync(1, 256);
+    if (threadIdx.x == 64) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) tma_store_2d(&tmO, smP + c * 16384, colQ + c * 64, row0);
+      tma_commit_group();
+      tma_wait_group<0>();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+
+// =====================================================================================
+// Backward.  One CTA per (batch, head, 128-key block j); K_j and V_j stay resident in smem and the
+// CTA walks the query blocks i >= j.  Per (i, j) pair, five tcgen05 GEMMs:
+//     S  = Q_i K_j^T                    -> TMEM[0:128)         (softmax recomputed from the saved LSE)
+//     dP = dO_i V_j^T                   -> TMEM[128:256)
+//     dV += P~^T dO_i   (P~ = dropout(P) from smem, consumed MN-major)   -> TMEM[256:256+HD)
+//     dK += dS^T Q_i    (dS = P o (D o dP / keep - delta) * scale)        -> TMEM[384:384+HD)
+//     dQ_i += dS K_j    -> TMEM[0:HD) (reuses the S columns) -> fp32 smem -> TMA reduce-add
+// Softmax threads own one query row each (same mapping and Philox stream as forward).
+template <int HD>
+struct AttnBwdSmem {
+  static constexpr int CH = HD / 64;
+  static constexpr int TILE = 128 * 128 * CH;
+  static constexpr int K_OFF = 0, V_OFF = TILE, Q_OFF = 2 * TILE, DO_OFF = 3 * TILE;
+  static constexpr int P_OFF = 4 * TILE;            // 32 KB: P~ (bf16) / dQ staging (fp32) / dV staging
+  static constexpr int DS_OFF = 4 * TILE + 32768;   // 32 KB: dS (bf16) / dK staging
+  static constexpr int BAR_OFF = 4 * TILE + 65536;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+struct AttnBwdParams {
+  int B, T, H;
+  float scale_log2, scale;
+  const float* slopes;
+  const float* lse;      // [B,H,T]
+  const float* delta;    // [B,H,T] rowsum(dO o O)
+  uint32_t drop_thr8;
+  float inv_keep;
+  const uint64_t* rng;
+  uint32_t op_id;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const __grid_constant__ CUtensorMap tmDQKV, const __grid_constant__ CUtensorMap tmDQacc, const AttnBwdParams p) {
+  using L = AttnBwdSmem<HD>;
+  constexpr int CH = L::CH;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smK = smem + L::K_OFF;
+  uint8_t* smV = smem + L::V_OFF;
+  uint8_t* smQ = smem + L::Q_OFF;
+  uint8_t* smDO = smem + L::DO_OFF;
+  uint8_t* smP = smem + L::P_OFF;
+  uint8_t* smDS = smem + L::DS_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* kv_full = bars;        // TMA -> MMA (once)
+  uint64_t* q_full = bars + 1;     // TMA -> MMA
+  uint64_t* do_full = bars + 2;    // TMA -> MMA
+  uint64_t* qdo_empty = bars + 3;  // MMA commit -> TMA
+  uint64_t* s_full = bars + 4;     // MMA -> softmax
+  uint64_t* dp_full = bars + 5;    // MMA -> softmax
+  uint64_t* dp_empty = bars + 6;   // softmax(128) -> MMA
+  uint64_t* p_ready = bars + 7;    // softmax(128) -> MMA
+  uint64_t* ds_ready = bars + 8;   // softmax(128) -> MMA
+  uint64_t* pdv_done = bars + 9;   // MMA commit -> softmax (P smem free)
+  uint64_t* dq_full = bars + 10;   // MMA commit -> softmax
+  uint64_t* dq_drained = bars + 11;  // softmax(128) -> MMA (S/dQ columns free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jb = blockIdx.x;                   // key block (low j = most work, scheduled first)
+  const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  const int D = p.H * HD;
+  const int nq = p.T / ATT_BM;
+  const int niter = nq - jb;                   // query blocks jb..nq-1
+  const int krow = b * p.T + jb * ATT_BN;
+  const int colQ = h * HD, colK = D + h * HD, colV = 2 * D + h * HD;
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmQKV); prefetch_tmap(&tmDO); prefetch_tmap(&tmDQKV); prefetch_tmap(&tmDQacc); }
+  if (warp == 1 && lane == 0) {
+    mbar_init(kv_full, 1); mbar_init(q_full, 1); mbar_init(do_full, 1); mbar_init(qdo_empty, 1);
+    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(dp_empty, 256); mbar_init(p_ready, 256);
+    mbar_init(ds_ready, 256); mbar_init(pdv_done, 1); mbar_init(dq_full, 1); mbar_init(dq_drained, 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * L::TILE);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        tma_load_2d(smK + c * 16384, &tmQKV, kv_full, colK + c * 64, krow);
+        tma_load_2d(smV + c * 16384, &tmQKV, kv_full, colV + c * 64, krow);
+      }
+      for (int it = 0; it < niter; ++it) {
+        const int qrow = b * p.T + (jb + it) * ATT_BM;
+        mbar_wait(qdo_empty, (it & 1) ^ 1);
+        mbar_expect_tx(q_full, L::TILE);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) tma_load_2d(smQ + c * 16384, &tmQKV, q_full, colQ + c * 64, qrow);
+        mbar_expect_tx(do_full, L::TILE);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) tma_load_2d(smDO + c * 16384, &tmDO, do_full, colQ + c * 64, qrow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_t = make_idesc_bf16(128, HD, 1, 1);   // dV, dK: both operands MN-major
+      constexpr uint32_t idesc_q = make_idesc_bf16(128, HD, 0, 1);   // dQ: dS K-major, K_j MN-major
+      const uint32_t k_addr = smem_u32(smK), v_addr = smem_u32(smV), q_addr = smem_u32(smQ), do_addr = smem_u32(smDO);
+      const uint32_t p_addr = smem_u32(smP), ds_addr = smem_u32(smDS);
+      mbar_wait(kv_full, 0);
+      for (int it = 0; it < niter; ++it) {
+        const uint32_t ph = it & 1;
+        // S = Q K^T
+        mbar_wait(q_full, ph);
+        mbar_wait(dq_drained, ph ^ 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+          umma_f16_ss(tS, make_smem_desc(q_addr + off, 16, 1024, kSwizzle128B), make_smem_desc(k_addr + off, 16, 1024, kSwizzle128B), idesc_s, k != 0);
+        }
+        umma_commit(s_full);
+        // dP = dO V^T
+        mbar_wait(do_full, ph);
+        mbar_wait(dp_empty, ph ^ 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+          umma_f16_ss(tDP, make_smem_desc(do_addr + off, 16, 1024, kSwizzle128B), make_smem_desc(v_addr + off, 16, 1024, kSwizzle128B), idesc_s, k != 0);
+        }
+        umma_commit(dp_full);
+        // dV += P~^T dO
+        mbar_wait(p_ready, ph);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_f16_ss(tDV, make_smem_desc(p_addr + k * 2048, 16384, 1024, kSwizzle128B),
+                      make_smem_desc(do_addr + k * 2048, 16384, 1024, kSwizzle128B), idesc_t, (it | k) != 0);
+        umma_commit(pdv_done);
+        // dK += dS^T Q ;  dQ = dS K
+        mbar_wait(ds_ready, ph);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_f16_ss(tDK, make_smem_desc(ds_addr + k * 2048, 16384, 1024, kSwizzle128B),
+                      make_smem_desc(q_addr + k * 2048, 16384, 1024, kSwizzle128B), idesc_t, (it | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_f16_ss(tS, make_smem_desc(ds_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, kSwizzle128B),
+                      make_smem_desc(k_addr + k * 2048, 16384, 1024, kSwizzle128B), idesc_q, k != 0);
+        umma_commit(dq_full);
+        umma_commit(qdo_empty);
+      }
+    }
+  } else {
+    // thread = (query row r = TMEM lane, column half hf) as in the forward kernel
+    const int sw = warp - 2;
+    const int quarter = warp & 3;
+    const int hf = sw >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int etid = threadIdx.x - 64;
+    const float slope2 = p.slopes ? p.slopes[h] * 1.4426950408889634f : 0.f;
+    const bool use_drop = p.drop_thr8 != 0;
+    const float keep_scale = use_drop ? p.inv_keep : 1.f;
+    uint64_t seed = 0, stream = 0;
+    if (use_drop) { seed = p.rng[0]; stream = p.rng[1] * 65536ull + p.op_id; }
+    Philox ph(seed);
+    const int kv0 = jb * ATT_BN + hf * 64;
+    const int cmax = r - hf * 64;
+    uint8_t* stage = hf == 0 ? smP : smDS;   // dQ staging: half 0 -> P buffer, half 1 -> dS buffer
+    for (int it = 0; it < niter; ++it) {
+      const uint32_t phs = it & 1;
+      const int qb = jb + it;
+      const int qi = qb * ATT_BM + r;
+      const size_t ridx = (size_t)bh * p.T + qi;
+      const float lse2 = p.lse[ridx] * 1.4426950408889634f;
+      const float delta = p.delta[ridx];
+      const uint64_t row_id = (uint64_t)bh * p.T + qi;
+      // ---- P = exp2(S*c + alibi - lse)
+      mbar_wait(s_full, phs);
+      tc_fence_after_sync();
+      float s[64];
+      {
+        uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+        tmem_ld_32x32b_x32(tS + lane_addr + hf * 64, sr);
+        tmem_ld_32x32b_x32(tS + lane_addr + hf * 64 + 32, sr + 32);
+        tmem_wait_ld();
+      }
+      const float base = slope2 * (float)(kv0 - qi) - lse2;
+      const bool diag = (it == 0);
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        float v = ex2_ftz(fmaf(s[c], p.scale_log2, fmaf(slope2, (float)c, base)));
+        s[c] = (diag && c > cmax) ? 0.f : v;
+      }
+      uint32_t keep[2] = {0xffffffffu, 0xffffffffu};  // bit c set = keep
+      if (use_drop) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 rb = attn_dropout_bits(ph, row_id, (uint32_t)(jb * 8 + hf * 4 + g), stream);
+          uint32_t w[4] = {rb.x, rb.y, rb.z, rb.w};
+          uint32_t bits = 0;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) bits |= (((w[e >> 2] >> ((e & 3) * 8)) & 0xFF) >= p.drop_thr8 ? 1u : 0u) << e;
+          if (g & 1) keep[g >> 1] = (keep[g >> 1] & 0xffffu) | (bits << 16); else keep[g >> 1] = bits | 0xffff0000u;
+        }
+      }
+      // ---- P~ -> smem chunk hf
+      {
+        uint8_t* prow = smP + hf * 16384 + r * 128;
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c16 * 8 + e * 2;
+            float a0 = ((keep[c >> 5] >> (c & 31)) & 1u) ? s[c] * keep_scale : 0.f;
+            float a1 = ((keep[(c + 1) >> 5] >> ((c + 1) & 31)) & 1u) ? s[c + 1] * keep_scale : 0.f;
+            pk[e] = pack_bf16(a0, a1);
+          }
+          *reinterpret_cast<uint4*>(prow + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(p_ready);
+      // ---- dS = P o (D o dP / keep - delta) * scale  -> smem chunk hf
+      mbar_wait(dp_full, phs);
+      tc_fence_after_sync();
+      {
+        uint8_t* drow = smDS + hf * 16384 + r * 128;
+#pragma unroll
+        for (int c32 = 0; c32 < 2; ++c32) {
+          uint32_t dpv[32];
+          tmem_ld_32x32b_x32(tDP + lane_addr + hf * 64 + c32 * 32, dpv);
+          tmem_wait_ld();
+          if (c32 == 1) { tc_fence_before_sync(); mbar_arrive(dp_empty); }
+          const uint32_t kb = keep[c32];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int cc = q4 * 8 + e * 2;
+              float d0 = ((kb >> cc) & 1u) ? __uint_as_float(dpv[cc]) * keep_scale : 0.f;
+              float d1 = ((kb >> (cc + 1)) & 1u) ? __uint_as_float(dpv[cc + 1]) * keep_scale : 0.f;
+              pk[e] = pack_bf16(s[c32 * 32 + cc] * (d0 - delta) * p.scale, s[c32 * 32 + cc + 1] * (d1 - delta) * p.scale);
+            }
+            const int c16 = c32 * 4 + q4;
+            *reinterpret_cast<uint4*>(drow + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(ds_ready);
+      // ---- drain dQ: each half moves HD/2 fp32 columns TMEM -> its staging buffer -> TMA reduce-add.
+      // P buffer is free once the dV MMA retired, dS buffer once dK/dQ retired (dq_full).
+      mbar_wait(pdv_done, phs);
+      mbar_wait(dq_full, phs);
+      tc_fence_after_sync();
+      const int qrow0 = b * p.T + qb * ATT_BM;
+      constexpr int QC = HD / 2;  // dQ columns per thread
+#pragma unroll
+      for (int c32 = 0; c32 < QC / 32; ++c32) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tS + lane_addr + hf * QC + c32 * 32, o);
+        tmem_wait_ld();
+        uint8_t* orow = stage + c32 * 16384 + r * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4)
+          *reinterpret_cast<uint4*>(orow + ((q4 ^ (r & 7)) << 4)) = make_uint4(o[q4 * 4], o[q4 * 4 + 1], o[q4 * 4 + 2], o[q4 * 4 + 3]);
+      }
+      tc_fence_before_sync();
+      mbar_arrive(dq_drained);
+      fence_proxy_async_smem();
+      named_bar_sync(2, 256);
+      if (etid == 0) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int c32 = 0; c32 < QC / 32; ++c32)
+            tma_reduce_add_2d(&tmDQacc, (hh == 0 ? smP : smDS) + c32 * 16384, colQ + hh * QC + c32 * 32, qrow0);
+        tma_commit_group();
+        tma_wait_group_read<0>();
+      }
+      named_bar_sync(1, 256);  // staging buffers reusable as P / dS by the next iteration
+    }
+    // ---- epilogue: dV, dK (TMEM) -> bf16 -> smem -> TMA store into the V / K slots of dqkv
+    mbar_wait(dq_full, (niter - 1) & 1);  // last commit covers every MMA
+    tc_fence_after_sync();
+    constexpr int OC = HD / 2;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t tsrc = which == 0 ? tDV : tDK;
+      uint8_t* stg = which == 0 ? smP : smDS;
+#pragma unroll
+      for (int c = 0; c < OC / 32; ++c) {
+        uint32_t o[32];
+        const int col = hf * OC + c * 32;
+        tmem_ld_32x32b_x32(tsrc + lane_addr + col, o);
+        tmem_wait_ld();
+        uint8_t* orow = stg + (col >> 6) * 16384 + r * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 o4 = make_uint4(pack_bf16(__uint_as_float(o[q4 * 8 + 0]), __uint_as_float(o[q4 * 8 + 1])),
+                                pack_bf16(__uint_as_float(o[q4 * 8 + 2]), __uint_as_float(o[q4 * 8 + 3])),
+                                pack_bf16(__uint_as_float(o[q4 * 8 + 4]), __uint_as_float(o[q4 * 8 + 5])),
+                                pack_bf16(__uint_as_float(o[q4 * 8 + 6]), __uint_as_float(o[q4 * 8 + 7])));
+          *reinterpret_cast<uint4*>(orow + (((((col & 63) >> 3) + q4) ^ (r & 7)) << 4)) = o4;
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2, 256);
+      if (etid == 0) {
+        const int col = which == 0 ? colV : colK;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) tma_store_2d(&tmDQKV, stg + c * 16384, col + c * 64, krow);
+        tma_commit_group();
+      }
+    }
+    if (etid == 0) tma_wait_group<0>();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// delta[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]   (one warp per (b,t,h) row)
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout,
+                                                         float* __restrict__ delta, int B, int T, int H, int hd) {
+  int row = blockIdx.x * 8 + (threadIdx.x >> 5);  // over B*T*H
+  if (row >= B * T * H) return;
+  int lane = threadIdx.x & 31;
+  int h = row % H, bt = row / H, t = bt % T, b = bt / T;
+  const bf162* po = reinterpret_cast<const bf162*>(o + (size_t)row * hd);
+  const bf162* pd = reinterpret_cast<const bf162*>(dout + (size_t)row * hd);
+  float acc = 0.f;
+  for (int c = lane; c < hd / 2; c += 32) {
+    float2 a = __bfloat1622float2(po[c]), d = __bfloat1622float2(pd[c]);
+    acc += a.x * d.x + a.y * d.y;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) delta[((size_t)b * H + h) * T + t] = acc;
+}
+
+// dqkv[:, 0:D] = bf16(dq_acc)
+__global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dqkv, size_t rows, int D8) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < rows * D8; i += (size_t)gridDim.x * blockDim.x) {
+    size_t rrow = i / D8;
+    int c = (int)(i % D8);
+    const float4* src = reinterpret_cast<const float4*>(acc + (rrow * D8 + c) * 8);
+    float4 a = src[0], b2 = src[1];
+    st_v4(dqkv + rrow * (size_t)D8 * 24 + (size_t)c * 8, make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b2.x, b2.y), pack_bf16(b2.z, b2.w)));
+  }
+}
+
+}  // namespace ztb
+
+using namespace ztb;
+
+int ztb_make_tmap_2d(CUtensorMap* tm, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
+                     int box_cols, int box_rows);
+
+template <int HD>
+static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& to, const AttnParams& p, cudaStream_t st) {
+  auto kern = attn_fwd_kernel<HD>;
+  static bool configured = false;
+  if (!configured) {
+    ZTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<HD>::TOTAL));
+    configured = true;
+  }
+  dim3 grid(p.T / ATT_BM, p.B * p.H);
+  kern<<<grid, ATT_THREADS, AttnSmem<HD>::TOTAL, st>>>(tq, to, p);
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// qkv: [B*T, 3*H*hd] bf16 (q | k | v, heads contiguous inside each); out: [B*T, H*hd]; lse: [B, H, T]
+int ztb_attn_fwd(const void* qkv, void* out, float* lse, const float* slopes, int B, int T, int H, int hd, float scale,
+                 float dropout_p, const uint64_t* rng, uint32_t op_id, cudaStream_t st) {
+  if (T % 128 != 0 || (hd != 64 && hd != 128)) {
+    ztb_set_error("ztb_attn_fwd", "needs T % 128 == 0 and head_dim in {64, 128}", __FILE__, __LINE__);
+    return -1;
+  }
+  const long long D = (long long)H * hd;
+  CUtensorMap tq, to;
+  int rc = ztb_make_tmap_2d(&tq, qkv, 2, (long long)B * T, 3 * D, 3 * D, 64, 128);
+  if (rc) return rc;
+  rc = ztb_make_tmap_2d(&to, out, 2, (long long)B * T, D, D, 64, 128);
+  if (rc) return rc;
+  AttnParams p;
+  p.B = B; p.T = T; p.H = H;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.slopes = slopes; p.lse = lse;
+  uint32_t thr = (uint32_t)(dropout_p * 256.f + 0.5f);
+  if (thr > 255) thr = 255;
+  p.drop_thr8 = dropout_p > 0.f ? (thr ? thr : 1) : 0;
+  p.inv_keep = 256.f / (256.f - (float)p.drop_thr8);
+  p.rng = rng; p.op_id = op_id;
+  if (p.drop_thr8 && !rng) { ztb_set_error("ztb_attn_fwd", "dropout needs rng", __FILE__, __LINE__); return -1; }
+  return hd == 128 ? launch_fwd<128>(tq, to, p, st) : launch_fwd<64>(tq, to, p, st);
+}
+
+
+template <int HD>
+static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tdqkv, const CUtensorMap& tacc,
+                      const AttnBwdParams& p, cudaStream_t st) {
+  auto kern = attn_bwd_kernel<HD>;
+  static bool configured = false;
+  if (!configured) {
+    ZTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnBwdSmem<HD>::TOTAL));
+    configured = true;
+  }
+  dim3 grid(p.T / ATT_BN, p.B * p.H);
+  kern<<<grid, ATT_THREADS, AttnBwdSmem<HD>::TOTAL, st>>>(tq, tdo, tdqkv, tacc, p);
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// dqkv: [B*T, 3*D] bf16 (written in full); dq_acc: [B*T, D] fp32 scratch, must be zero on entry;
+// delta: [B,H,T] fp32 scratch.
+int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dq_acc, float* delta,
+                 const float* slopes, int B, int T, int H, int hd, float scale, float dropout_p, const uint64_t* rng,
+                 uint32_t op_id, int sms, cudaStream_t st) {
+  if (T % 128 != 0 || (hd != 64 && hd != 128)) {
+    ztb_set_error("ztb_attn_bwd", "needs T % 128 == 0 and head_dim in {64, 128}", __FILE__, __LINE__);
+    return -1;
+  }
+  const long long D = (long long)H * hd, rows = (long long)B * T;
+  attn_delta_kernel<<<(unsigned)((rows * H + 7) / 8), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, T, H, hd);
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  CUtensorMap tq, tdo, tdqkv, tacc;
+  int rc = ztb_make_tmap_2d(&tq, qkv, 2, rows, 3 * D, 3 * D, 64, 128);
+  if (rc) return rc;
+  rc = ztb_make_tmap_2d(&tdo, dout, 2, rows, D, D, 64, 128);
+  if (rc) return rc;
+  rc = ztb_make_tmap_2d(&tdqkv, dqkv, 2, rows, 3 * D, 3 * D, 64, 128);
+  if (rc) return rc;
+  rc = ztb_make_tmap_2d(&tacc, dq_acc, 4, rows, D, D, 32, 128);
+  if (rc) return rc;
+  AttnBwdParams p;
+  p.B = B; p.T = T; p.H = H;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  p.slopes = slopes; p.lse = lse; p.delta = delta;
+  uint32_t thr = (uint32_t)(dropout_p * 256.f + 0.5f);
+  if (thr > 255) thr = 255;
+  p.drop_thr8 = dropout_p > 0.f ? (thr ? thr : 1) : 0;
+  p.inv_keep = 256.f / (256.f - (float)p.drop_thr8);
+  p.rng = rng; p.op_id = op_id;
+  rc = hd == 128 ? launch_bwd<128>(tq, tdo, tdqkv, tacc, p, st) : launch_bwd<64>(tq, tdo, tdqkv, tacc, p, st);
+  if (rc) return rc;
+  size_t n = (size_t)rows * (D / 8);
+  size_t g = (n + 255) / 256;
+  if (g > (size_t)sms * 8) g = (size_t)sms * 8;
+  attn_dq_convert_kernel<<<(unsigned)g, 256, 0, st>>>(dq_acc, (bf16*)dqkv, (size_t)rows, (int)(D / 8));
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -181,6 +181,38 @@ void adamw_shard(at::Tensor& master, at::Tensor& m, at::Tensor& v, at::Tensor& f
 
 int64_t segment_struct_size() { return sizeof(ZtbSegment); }
 
+// qkv: (B, T, 3*H*hd) bf16 packed [q | k | v]; returns (out (B,T,H*hd) bf16, lse (B,H,T) fp32)
+std::vector<at::Tensor> attention_fwd(const at::Tensor& qkv, const c10::optional<at::Tensor>& slopes, int64_t H, double scale,
+                                      double p, const c10::optional<at::Tensor>& rng, int64_t op_id) {
+  need(is_bf16_cuda(qkv) && qkv.dim() == 3 && qkv.is_contiguous(), "attention_fwd: qkv must be (B,T,3D) bf16 contiguous");
+  c10::cuda::CUDAGuard g(qkv.device());
+  int B = qkv.size(0), T = qkv.size(1), D = qkv.size(2) / 3, hd = D / H;
+  auto out = at::empty({B, T, D}, qkv.options());
+  auto lse = at::empty({B, (int)H, T}, qkv.options().dtype(at::kFloat));
+  const float* sl = nullptr;
+  if (slopes.has_value()) { need(slopes->is_cuda() && slopes->scalar_type() == at::kFloat && slopes->numel() == H, "attention_fwd: slopes fp32 [H]"); sl = slopes->data_ptr<float>(); }
+  const uint64_t* r = rng.has_value() ? (const uint64_t*)rng->data_ptr<int64_t>() : nullptr;
+  check(ztb_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), sl, B, T, (int)H, hd, (float)scale, (float)p, r, (uint32_t)op_id, stream()), "attention_fwd");
+  return {out, lse};
+}
+
+at::Tensor attention_bwd(const at::Tensor& qkv, const at::Tensor& out, const at::Tensor& dout, const at::Tensor& lse,
+                         const c10::optional<at::Tensor>& slopes, int64_t H, double scale, double p,
+                         const c10::optional<at::Tensor>& rng, int64_t op_id) {
+  need(is_bf16_cuda(qkv) && qkv.dim() == 3 && qkv.is_contiguous() && is_bf16_cuda(out) && out.is_contiguous() && is_bf16_cuda(dout) && dout.is_contiguous(),
+       "attention_bwd: bf16 contiguous tensors");
+  c10::cuda::CUDAGuard g(qkv.device());
+  int B = qkv.size(0), T = qkv.size(1), D = qkv.size(2) / 3, hd = D / H;
+  auto dqkv = at::empty_like(qkv);
+  auto acc = at::zeros({(int64_t)B * T, D}, qkv.options().dtype(at::kFloat));
+  auto delta = at::empty({B, (int)H, T}, qkv.options().dtype(at::kFloat));
+  const float* sl = slopes.has_value() ? slopes->data_ptr<float>() : nullptr;
+  const uint64_t* r = rng.has_value() ? (const uint64_t*)rng->data_ptr<int64_t>() : nullptr;
+  check(ztb_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr<float>(), dqkv.data_ptr(), acc.data_ptr<float>(),
+                     delta.data_ptr<float>(), sl, B, T, (int)H, hd, (float)scale, (float)p, r, (uint32_t)op_id, num_sms(), stream()), "attention_bwd");
+  return dqkv;
+}
+
 std::vector<void*> to_ptrs(const std::vector<int64_t>& v) {
   std::vector<void*> o;
   for (auto x : v) o.push_back(reinterpret_cast<void*>(x));
@@ -232,6 +264,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("accumulate") = false, py::arg("a_mn") = false, py::arg("b_mn") = false);
   m.def("adamw_shard", &adamw_shard);
   m.def("segment_struct_size", &segment_struct_size);
+  m.def("attention_fwd", &attention_fwd);
+  m.def("attention_bwd", &attention_bwd);
   m.def("signal", &signal);
   m.def("allgather_pull", &allgather_pull);
   m.def("reduce_scatter", &reduce_scatter);

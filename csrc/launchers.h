@@ -64,3 +64,10 @@ int ztb_allgather_pull(void* dst, void* const* srcs, int world, const ZtbSegment
 int ztb_reduce_scatter(void* out, void* const* grads, int n_peers, const ZtbSegment* segs, int nseg, long long total_tiles,
                        const int* flags, int wait_value, int sms, cudaStream_t st);
 int ztb_p2p_copy(void* dst, const void* src, size_t bytes, int sms, cudaStream_t st);
+
+// ---- attention.cu (tcgen05 ALiBi causal flash attention)
+int ztb_attn_fwd(const void* qkv, void* out, float* lse, const float* slopes, int B, int T, int H, int hd, float scale,
+                 float dropout_p, const uint64_t* rng, uint32_t op_id, cudaStream_t st);
+int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dq_acc, float* delta,
+                 const float* slopes, int B, int T, int H, int hd, float scale, float dropout_p, const uint64_t* rng,
+                 uint32_t op_id, int sms, cudaStream_t st);

@@ -1,0 +1,37 @@
+"""Autograd wrapper of the tcgen05 ALiBi flash-attention kernels (csrc/attention.cu)."""
+from __future__ import annotations
+
+import torch
+
+from . import cuda as K
+
+
+def supported(qkv: torch.Tensor, n_head: int) -> bool:
+    B, T, D3 = qkv.shape
+    hd = D3 // 3 // n_head
+    return qkv.dtype == torch.bfloat16 and T % 128 == 0 and hd in (64, 128)
+
+
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, slopes, n_head, scale, p):
+        qkv = qkv.contiguous()
+        rng = K.rng_state(qkv.device)
+        op_id = K._next_op_id() if p > 0 else 0
+        sl = slopes.float().contiguous() if slopes is not None else None
+        out, lse = K._C.attention_fwd(qkv, sl, n_head, scale, p, rng if p > 0 else None, op_id)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.meta = (sl, n_head, scale, p, op_id)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        sl, n_head, scale, p, op_id = ctx.meta
+        rng = K.rng_state(qkv.device)
+        dqkv = K._C.attention_bwd(qkv, out, dout.contiguous(), lse, sl, n_head, scale, p, rng if p > 0 else None, op_id)
+        return dqkv, None, None, None, None
+
+
+def alibi_attention(qkv, slopes, n_head, scale, p):
+    return _Attention.apply(qkv, slopes, n_head, scale, float(p))

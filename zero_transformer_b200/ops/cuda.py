@@ -419,10 +419,13 @@ def cross_entropy(logits, labels):
 # ---------------------------------------------------------------------------
 def attention(qkv, slopes, n_head, scale, p, training):
     impl = CONFIG.attn_impl
-    if impl in ("auto", "tc") and hasattr(_C._mod, "attention_fwd"):
-        from .attention_cuda import alibi_attention
+    if impl in ("auto", "tc"):
+        from .attention_cuda import alibi_attention, supported
 
-        return alibi_attention(qkv, slopes, n_head, scale, p if training else 0.0)
+        if supported(qkv, n_head):
+            return alibi_attention(qkv, slopes, n_head, scale, p if training else 0.0)
+        if impl == "tc":
+            raise RuntimeError("tcgen05 attention needs bf16, T % 128 == 0 and head_dim in {64, 128}")
     if impl in ("auto", "flash"):
         from flash_attn import flash_attn_qkvpacked_func
 
