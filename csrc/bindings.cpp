@@ -225,6 +225,10 @@ void signal(std::vector<int64_t> pad_ptrs, int64_t slot, int64_t value) {
   check(ztb_signal(p.data(), (int)p.size(), (int)slot, (int)value, stream()), "signal");
 }
 
+void wait_flags(int64_t flags_ptr, int64_t n, int64_t value) {
+  check(ztb_wait_flags(reinterpret_cast<const int*>(flags_ptr), (int)n, (int)value, stream()), "wait_flags");
+}
+
 void allgather_pull(at::Tensor& flat_param, std::vector<int64_t> src_ptrs, const at::Tensor& segs, int64_t nseg, int64_t total_tiles,
                     int64_t flags_ptr, int64_t wait_value) {
   need(is_bf16_cuda(flat_param), "allgather_pull: bf16 flat_param");
@@ -267,6 +271,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_bwd", &attention_bwd);
   m.def("signal", &signal);
+  m.def("wait_flags", &wait_flags);
   m.def("allgather_pull", &allgather_pull);
   m.def("reduce_scatter", &reduce_scatter);
   m.def("p2p_copy", &p2p_copy);

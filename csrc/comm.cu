@@ -33,6 +33,15 @@ ZTB_DEVINL void st_release_sys_i32(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// 1-warp spin-wait on a row of flags.  Cross-rank waits that overlap with compute run here (one
+// tiny CTA) instead of inside the big kernels, so a stalled peer can never pin SM resources that
+// this rank's own backward needs to make progress.
+__global__ void wait_flags_kernel(const int* flags, int n, int value) {
+  if ((int)threadIdx.x < n) {
+    while (ld_acquire_sys_i32(flags + threadIdx.x) < value) __nanosleep(128);
+  }
+}
+
 __global__ void signal_kernel(PtrList pads, int n, int slot, int value) {
   if ((int)threadIdx.x < n) {
     __threadfence_system();
@@ -111,6 +120,12 @@ __global__ void __launch_bounds__(256) p2p_copy_kernel(uint4* __restrict__ dst, 
 }  // namespace ztb
 
 using namespace ztb;
+
+int ztb_wait_flags(const int* flags, int n, int value, cudaStream_t st) {
+  wait_flags_kernel<<<1, 32, 0, st>>>(flags, n, value);
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 int ztb_signal(void* const* pads, int n, int slot, int value, cudaStream_t st) {
   if (n < 1 || n > kMaxRanks) { ztb_set_error("ztb_signal", "bad rank count", __FILE__, __LINE__); return -1; }

@@ -59,6 +59,7 @@ int ztb_gemm(const ZtbGemmArgs* args, int sms, cudaStream_t st);
 
 // ---- comm.cu (NVLink peer-memory kernels; all pointers are device addresses, peers mapped via symmetric memory)
 int ztb_signal(void* const* pads, int n, int slot, int value, cudaStream_t st);
+int ztb_wait_flags(const int* flags, int n, int value, cudaStream_t st);
 int ztb_allgather_pull(void* dst, void* const* srcs, int world, const ZtbSegment* segs, int nseg, long long total_tiles,
                        const int* flags, int wait_value, int sms, cudaStream_t st);
 int ztb_reduce_scatter(void* out, void* const* grads, int n_peers, const ZtbSegment* segs, int nseg, long long total_tiles,

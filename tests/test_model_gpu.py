@@ -72,6 +72,7 @@ def test_fused_engine_trains_and_matches_plain_adamw_direction():
         eng.step()
     assert losses[-1] < losses[0] - 0.5, losses
     # bf16 working copy tracks the fp32 master shard
+    eng.synchronize()
     sh = eng.layout.gather_shard_from_flat(eng.flat_param, 0).float()
     torch.testing.assert_close(sh, eng.master, rtol=1e-2, atol=1e-3)
 
@@ -84,3 +85,31 @@ def test_dropout_changes_between_micro_steps_but_is_reproducible_in_backward():
     c = m.loss(x, train=False).item()
     d = m.loss(x, train=False).item()
     assert a != b and c == d
+
+
+def test_overlapped_engine_backward_matches_plain_path():
+    """engine.backward (lazy zero + per-bucket updates launched from backward hooks on the comm
+    stream) must give the same parameters as zero_grad + loss.backward + step."""
+    from zero_transformer_b200.optim.schedule import WarmupCosine
+    from zero_transformer_b200.parallel.zero1 import Zero1Engine
+
+    outs = []
+    for overlapped in (False, True):
+        m, _, cfg = _models(dropout=0.0)
+        m = m.float()
+        eng = Zero1Engine(m, lr_fn=WarmupCosine(2e-3, 0, 100, 1e-4), backend="fused", grad_accum_steps=2)
+        g = torch.Generator().manual_seed(3)
+        for _ in range(4):
+            x = torch.randint(0, cfg.vocab_size, (8, 256), generator=g, dtype=torch.int32).cuda()
+            eng.zero_grad(lazy=overlapped)
+            for k, mb in enumerate(x.chunk(2)):
+                loss = m.loss(mb, train=False)
+                if overlapped:
+                    eng.backward(loss, last=(k == 1))
+                else:
+                    loss.backward()
+            eng.step()
+        eng.synchronize()
+        outs.append((eng.master.clone(), eng.flat_param.clone()))
+    rel = (outs[0][0] - outs[1][0]).norm() / outs[0][0].norm()
+    assert rel < 5e-3, rel.item()  # embedding-gradient atomics are order-nondeterministic; Adam amplifies near-zero grads

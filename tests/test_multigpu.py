@@ -40,12 +40,13 @@ def _worker(rank, world, port, backend, out):
         for _ in range(4):
             b = torch.randint(0, CFG["vocab_size"], (4 * world, 256), generator=g, dtype=torch.int32)
             mine = b.view(2, world, 2, 256)[:, rank].reshape(4, 256).cuda()
-            eng.zero_grad()
-            for mb in mine.chunk(2):
+            eng.zero_grad(lazy=True)
+            for k, mb in enumerate(mine.chunk(2)):
                 l = model.loss(mb, train=False)
-                l.backward()
+                eng.backward(l, last=(k == 1))
             losses.append(l.item())
             eng.step()
+        eng.synchronize()
         torch.cuda.synchronize()
         # every rank must hold identical full parameters after the all-gather
         flat = eng.flat_param.float()

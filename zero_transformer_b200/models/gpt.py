@@ -156,6 +156,10 @@ class Transformer(nn.Module):
         nn.init.normal_(self.wte.weight, mean=0.0, std=0.02)
         self.blocks = nn.ModuleList([TransformerBlock(cfg) for _ in range(cfg.N)])
         self.ln_f = LayerNorm(cfg.embedding_dim, cfg.ln_eps)
+        # optional ZeRO-1 engine hooks: called with the block index right before block i runs in
+        # forward (parameter prefetch wait) and right after its backward finished (bucket ready)
+        self.block_forward_pre_hook = None
+        self.block_backward_done_hook = None
 
     # -- the reference keeps these as constructor attributes
     @property
@@ -173,6 +177,10 @@ class Transformer(nn.Module):
         presents = []
         for i, blk in enumerate(self.blocks):
             past = past_states[i] if past_states is not None else None
+            if self.block_forward_pre_hook is not None:
+                self.block_forward_pre_hook(i)
+            if self.block_backward_done_hook is not None and h.requires_grad:
+                h.register_hook(lambda g, i=i: self.block_backward_done_hook(i))
             h, present = blk(h, train, past, use_cache)
             presents.append(present)
         return self.ln_f(h), presents

@@ -71,6 +71,12 @@ class _Config:
 
 CONFIG = _Config()
 
+# Gradient write mode for parameters that already own a ``.grad`` buffer (the ZeRO-1 flat gradient
+# buffer): accumulate (beta = 1) or overwrite (beta = 0).  The engine switches to overwrite for the
+# first micro-batch of a step, which removes the gradient memset and the read half of the first
+# accumulation.
+GRAD_MODE = {"accumulate": True}
+
 # ---------------------------------------------------------------------------
 # Dropout RNG: one device-resident (seed, offset) pair per device so the whole
 # step is CUDA-graph capturable.  Each dropout site of a forward pass gets a
@@ -140,10 +146,13 @@ def _mm_wgrad(dy: torch.Tensor, x2: torch.Tensor, w: torch.Tensor) -> Optional[t
     K = x2.shape[1]
     tc = CONFIG.tc_gemm_bwd and _tc_ok(N, K, M) and N % 8 == 0
     if CONFIG.fuse_wgrad and w.grad is not None and w.grad.is_contiguous():
+        acc = GRAD_MODE["accumulate"]
         if tc:
-            _C.gemm(dy, x2, C=w.grad, accumulate=True, a_mn=True, b_mn=True)
-        else:
+            _C.gemm(dy, x2, C=w.grad, accumulate=acc, a_mn=True, b_mn=True)
+        elif acc:
             w.grad.addmm_(dy.t(), x2) if w.grad.dtype == dy.dtype else w.grad.add_((dy.t() @ x2).to(w.grad.dtype))
+        else:
+            w.grad.copy_(dy.t() @ x2)
         return None
     if tc:
         return _C.gemm(dy, x2, a_mn=True, b_mn=True)
@@ -169,6 +178,12 @@ class _LayerNorm(torch.autograd.Function):
     def backward(ctx, dy):
         x, w, mean, rstd = ctx.saved_tensors
         dx, dw = _C.layernorm_bwd(dy.contiguous(), x, w.contiguous(), mean, rstd)
+        if CONFIG.fuse_wgrad and w.grad is not None:
+            if GRAD_MODE["accumulate"]:
+                w.grad.add_(dw)
+            else:
+                w.grad.copy_(dw)
+            return dx, None, None
         return dx, dw.to(w.dtype), None
 
 

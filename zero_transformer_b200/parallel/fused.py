@@ -72,6 +72,19 @@ class SymmetricBuffer:
 
 
 class FusedComm:
+    """Per-bucket fused reduce-scatter+AdamW and all-gather over NVLink peer memory.
+
+    Streams: everything here runs on a dedicated communication stream.  ``bucket_update(b)`` is
+    called from the backward pass as soon as bucket ``b``'s gradients are final (overlapping the
+    remaining backward); ``prefetch_all()`` queues the all-gather pulls in forward order so they
+    overlap the next forward; ``wait_bucket(b)`` makes the compute stream wait for bucket ``b``.
+
+    Flags (symmetric int32 pad, one row of ``MAX_RANKS`` per (kind, bucket)) carry the step number:
+      GRAD_READY[b][r]   rank r's gradients of bucket b are final      (consumed by every rank's AdamW)
+      SHARD_READY[b][r]  rank r has written its updated chunk of b     (consumed by every rank's pull)
+    Cross-rank waits run in a one-warp kernel so a slow peer never pins SM resources.
+    """
+
     def __init__(self, layout, rank: int, world: int, group, device, compute_dtype, grad_dtype):
         from ..ops._build import load
 
@@ -84,57 +97,99 @@ class FusedComm:
         self._C = load()
         self.layout, self.rank, self.world, self.group, self.device = layout, rank, world, group, device
         self.grad_fp32 = grad_dtype == torch.float32
+        self.nb = len(layout.buckets)
         self._param = SymmetricBuffer(layout.total, torch.bfloat16, device, group, world)
         self._grad = SymmetricBuffer(layout.total, grad_dtype, device, group, world)
-        self._flags = SymmetricBuffer(2 * MAX_RANKS, torch.int32, device, group, world)
+        self._flags = SymmetricBuffer(2 * self.nb * MAX_RANKS, torch.int32, device, group, world)
         self.flat_param, self.flat_grad = self._param.tensor, self._grad.tensor
-        # my chunk of every region (AdamW) and everybody else's chunks (all-gather)
-        segs = [(r.offset + rank * r.chunk, r.shard_offset, r.chunk, int(r.decay)) for r in layout.regions]
-        self.adam_segs, self.adam_tiles = pack_segments(segs, device, ADAM_TILE)
-        self.n_adam = len(segs)
-        pull = [(r.offset + p * r.chunk, 0, r.chunk, p) for p in range(world) if p != rank for r in layout.regions]
-        self.pull_segs, self.pull_tiles = pack_segments(pull, device, COPY_TILE)
-        self.n_pull = len(pull)
+        self.adam, self.pull = [], []
+        for b in layout.buckets:
+            segs = [(r.offset + rank * r.chunk, r.shard_offset, r.chunk, int(r.decay)) for r in b.regions]
+            t, tiles = pack_segments(segs, device, ADAM_TILE)
+            self.adam.append((t, len(segs), tiles))
+            pl = [(r.offset + p * r.chunk, 0, r.chunk, p) for p in range(world) if p != rank for r in b.regions]
+            t, tiles = pack_segments(pl, device, COPY_TILE)
+            self.pull.append((t, len(pl), tiles))
+        self.grad_ptrs = self._grad.ptrs[rank:] + self._grad.ptrs[:rank]  # local copy first
         self.epoch = 0
+        self.stream = torch.cuda.Stream(device)
+        self.ready = [torch.cuda.Event() for _ in range(self.nb)]       # bucket b usable by compute
+        self._ev = torch.cuda.Event()
+        self._pending = [False] * self.nb
         if world > 1:
             dist.barrier(group)
 
-    # device address of this rank's flag row for `kind`
-    def _my_flags(self, kind: int) -> int:
-        return self._flags.ptrs[self.rank] + 4 * kind * MAX_RANKS
+    # flag addressing ----------------------------------------------------
+    def _slot(self, kind: int, bucket: int, src: int) -> int:
+        return (kind * self.nb + bucket) * MAX_RANKS + src
 
-    def _signal(self, kind: int, value: int) -> None:
-        # slot (kind, my rank) in every rank's pad (mine included)
-        self._C.signal(self._flags.ptrs, kind * MAX_RANKS + self.rank, value)
+    def _my_row(self, kind: int, bucket: int) -> int:
+        return self._flags.ptrs[self.rank] + 4 * self._slot(kind, bucket, 0)
 
-    def step(self, *, master, m, v, lr, beta1, beta2, eps, wd, step, clip, grad_scale) -> None:
+    def _signal(self, kind: int, bucket: int, value: int) -> None:
+        self._C.signal(self._flags.ptrs, self._slot(kind, bucket, self.rank), value)
+
+    # per-step protocol --------------------------------------------------
+    def begin_step(self) -> None:
         self.epoch += 1
-        e = self.epoch
-        if self.world > 1:
-            self._signal(FLAG_GRAD_READY, e)
-            grad_ptrs = self._grad.ptrs[self.rank:] + self._grad.ptrs[: self.rank]  # start with the local copy
-            wait_ptr, wait_val = self._my_flags(FLAG_GRAD_READY), e
-        else:
-            grad_ptrs, wait_ptr, wait_val = self._grad.ptrs, 0, 0
-        self._C.adamw_shard(master, m, v, self.flat_param, grad_ptrs, self.grad_fp32, self.adam_segs, self.n_adam,
-                            self.adam_tiles, lr, beta1, beta2, eps, wd, clip, grad_scale, step, wait_ptr, wait_val)
-        if self.world > 1:
-            self._signal(FLAG_SHARD_READY, e)
-            self._C.allgather_pull(self.flat_param, self._param.ptrs, self.pull_segs, self.n_pull, self.pull_tiles,
-                                   self._my_flags(FLAG_SHARD_READY), e)
 
-    def all_gather_now(self) -> None:
-        """Out-of-band all-gather (checkpoint load): publish + pull under a fresh epoch."""
+    def bucket_update(self, b: int, *, master, m, v, lr, beta1, beta2, eps, wd, step, clip, grad_scale) -> None:
+        """Bucket ``b``'s gradients are final on the current (compute) stream: reduce-scatter them
+        from every peer, apply AdamW to the owned shard and publish the new bf16 chunk."""
+        e = self.epoch
+        cur = torch.cuda.current_stream(self.device)
+        self._ev.record(cur)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self._ev)
+            if self.world > 1:
+                self._signal(FLAG_GRAD_READY, b, e)
+                self._C.wait_flags(self._my_row(FLAG_GRAD_READY, b), self.world, e)
+            segs, n, tiles = self.adam[b]
+            self._C.adamw_shard(master, m, v, self.flat_param, self.grad_ptrs if self.world > 1 else self._grad.ptrs,
+                                self.grad_fp32, segs, n, tiles, lr, beta1, beta2, eps, wd, clip, grad_scale, step, 0, 0)
+            if self.world > 1:
+                self._signal(FLAG_SHARD_READY, b, e)
+            else:
+                self.ready[b].record(self.stream)
+        self._pending[b] = True
+
+    def prefetch_all(self) -> None:
+        """Queue the all-gather of every bucket (forward order) behind the updates."""
         if self.world == 1:
             return
-        self.epoch += 1
         e = self.epoch
+        with torch.cuda.stream(self.stream):
+            for b in range(self.nb):
+                self._C.wait_flags(self._my_row(FLAG_SHARD_READY, b), self.world, e)
+                segs, n, tiles = self.pull[b]
+                self._C.allgather_pull(self.flat_param, self._param.ptrs, segs, n, tiles, 0, 0)
+                self.ready[b].record(self.stream)
+
+    def wait_bucket(self, b: int) -> None:
+        """Compute stream waits until bucket ``b`` holds this step's parameters."""
+        if self._pending[b]:
+            torch.cuda.current_stream(self.device).wait_event(self.ready[b])
+            self._pending[b] = False
+
+    def wait_all(self) -> None:
+        for b in range(self.nb):
+            self.wait_bucket(b)
+
+    def all_gather_now(self) -> None:
+        """Out-of-band all-gather (checkpoint load): publish + pull everything under a fresh epoch."""
+        if self.world == 1:
+            return
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)
-        self._signal(FLAG_GRAD_READY, e)  # keep both counters in lock-step
-        self._signal(FLAG_SHARD_READY, e)
-        self._C.allgather_pull(self.flat_param, self._param.ptrs, self.pull_segs, self.n_pull, self.pull_tiles,
-                               self._my_flags(FLAG_SHARD_READY), e)
+        self.begin_step()
+        e = self.epoch
+        with torch.cuda.stream(self.stream):
+            for b in range(self.nb):
+                self._signal(FLAG_GRAD_READY, b, e)
+                self._signal(FLAG_SHARD_READY, b, e)
+        self._pending = [True] * self.nb
+        self.prefetch_all()
+        self.wait_all()
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)
 

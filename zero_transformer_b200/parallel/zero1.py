@@ -124,13 +124,75 @@ class Zero1Engine:
                 p.grad = L.view(self.flat_grad, n)
         self._named = named
         self._grad_shard = torch.zeros(L.shard_total, dtype=self.grad_dtype, device=dev) if backend != "fused" else None
+        # fused backend: overlap machinery (see parallel/fused.py)
+        self._overwrite_next = False   # first micro-batch of the step overwrites the gradient buffers
+        self._last_micro = True
+        self._updated = set()
+        self._embed_bucket = next((b.index for b in L.buckets if b.name == "embed"), None)
+        self._block_bucket = {}
+        for b in L.buckets:
+            if b.name.startswith("block"):
+                self._block_bucket[int(b.name[5:])] = b.index
+        if self._fused is not None and hasattr(model, "block_backward_done_hook"):
+            model.block_backward_done_hook = self._on_block_backward_done
+            model.block_forward_pre_hook = self._on_block_forward_pre
 
     # ------------------------------------------------------------------
     @property
     def lr(self) -> float:
         return float(self.lr_fn(self.step_count))
 
-    def zero_grad(self) -> None:
+    # -- fused-backend hooks ---------------------------------------------
+    def _adam_kwargs(self):
+        return dict(master=self.master, m=self.exp_avg, v=self.exp_avg_sq, lr=self.lr, beta1=self.beta1, beta2=self.beta2,
+                    eps=self.eps, wd=self.weight_decay, step=self.step_count + 1, clip=self.clip or 0.0,
+                    grad_scale=1.0 / (self.world * self.grad_accum_steps))
+
+    def _on_block_backward_done(self, i: int) -> None:
+        """Block ``i``'s backward just finished on the last micro-batch: its bucket's gradients are
+        final, so start reduce-scatter+AdamW for it now, overlapping the rest of backward."""
+        if not self._last_micro or not self._in_engine_backward:
+            return
+        b = self._block_bucket.get(i)
+        if b is not None and b not in self._updated:
+            self._fused.bucket_update(b, **self._adam_kwargs())
+            self._updated.add(b)
+
+    def _on_block_forward_pre(self, i: int) -> None:
+        b = self._block_bucket.get(i)
+        if b is not None:
+            self._fused.wait_bucket(b)
+
+    _in_engine_backward = False
+
+    def backward(self, loss: torch.Tensor, last: bool = True) -> None:
+        """``loss.backward()`` with the engine's gradient-buffer protocol: the first micro-batch after
+        ``zero_grad()`` overwrites the flat gradient buffer (no memset), later ones accumulate, and on
+        the ``last`` micro-batch every bucket's optimizer update starts as soon as its block's backward
+        is done.  Plain ``loss.backward()`` + ``step()`` remains valid (no overlap)."""
+        if self._fused is None:
+            loss.backward()
+            return
+        from ..ops import cuda as K
+
+        self._last_micro = bool(last)
+        if last and not self._updated:
+            self._fused.begin_step()
+        self._in_engine_backward = True
+        K.GRAD_MODE["accumulate"] = not self._overwrite_next
+        try:
+            loss.backward()
+        finally:
+            K.GRAD_MODE["accumulate"] = True
+            self._in_engine_backward = False
+        self._overwrite_next = False
+
+    def zero_grad(self, lazy: bool = False) -> None:
+        """``lazy=True`` (fused backend, gradients produced through ``engine.backward``): skip the
+        memset, the next backward overwrites instead of accumulating."""
+        if lazy and self._fused is not None:
+            self._overwrite_next = True
+            return
         self.flat_grad.zero_()
         # autograd may have replaced .grad if someone set it to None; re-point cheaply
         for n, p in self._named:
@@ -146,11 +208,19 @@ class Zero1Engine:
         t = self.step_count + 1
         scale = 1.0 / (self.world * self.grad_accum_steps)
         if self.backend == "fused":
-            self._fused.step(
-                master=self.master, m=self.exp_avg, v=self.exp_avg_sq,
-                lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps, wd=self.weight_decay,
-                step=t, clip=self.clip or 0.0, grad_scale=scale,
-            )
+            f = self._fused
+            if not self._updated:
+                f.begin_step()          # no bucket was started from backward (plain loss.backward())
+            kw = self._adam_kwargs()
+            for b in range(f.nb):       # whatever backward did not start: embed bucket, or everything
+                if b not in self._updated:
+                    f.bucket_update(b, **kw)
+            self._updated.clear()
+            f.prefetch_all()            # all-gather, queued in forward order, overlaps the next forward
+            if self._embed_bucket is not None:
+                f.wait_bucket(self._embed_bucket)
+            if not hasattr(self.model, "block_forward_pre_hook") or self.model.block_forward_pre_hook is None:
+                f.wait_all()
         else:
             self._reduce_to_shard()
             with torch.no_grad():
@@ -189,10 +259,18 @@ class Zero1Engine:
             src = self.flat_param[s:e] if inplace_ok else self.flat_param[s:e].clone()
             dist.all_gather_into_tensor(self.flat_param[r.offset: r.offset + r.padded], src, group=self.group)
 
+    def synchronize(self) -> None:
+        """Make the optimizer state and the parameters safe to read from the current stream / host
+        (the fused backend updates them on its own communication stream)."""
+        if self._fused is not None:
+            self._fused.wait_all()
+            torch.cuda.current_stream(self.device).synchronize()
+
     # -- state -----------------------------------------------------------
     def shard_state(self) -> Dict[str, object]:
         """This rank's optimizer shard (what the reference keeps sharded on
         device, ``main_zero.py:447-450``)."""
+        self.synchronize()
         return {
             "step": self.step_count, "rank": self.rank, "world": self.world,
             "master": self.master.detach().cpu(), "exp_avg": self.exp_avg.detach().cpu(),
@@ -214,6 +292,7 @@ class Zero1Engine:
         ``main_zero.py:554-557``).  World-size independent, so a run can resume
         on a different number of GPUs."""
         L = self.layout
+        self.synchronize()
         out = {"step": self.step_count, "params": {}, "exp_avg": {}, "exp_avg_sq": {}}
         for key, shard in (("params", self.master), ("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
             if self.world > 1:

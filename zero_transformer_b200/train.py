@@ -131,11 +131,11 @@ class Trainer:
         batch already on the device.  Returns device tensors (no host sync)."""
         self.model.train()
         mbs = to_micro_batches(rechunk(batch, self.train_context), self.accum)
-        self.engine.zero_grad()
+        self.engine.zero_grad(lazy=True)
         loss_sum = None
         for i in range(self.accum):
             loss = self.model.loss(mbs[i], train=True)
-            loss.backward()
+            self.engine.backward(loss, last=(i == self.accum - 1))
             loss_sum = loss.detach() if loss_sum is None else loss_sum + loss.detach()
         lr = self.engine.step()
         mean_loss = loss_sum / self.accum
