@@ -158,6 +158,32 @@ at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tens
   return C;
 }
 
+// Forward GEMM C = A * B^T with the ZeRO-1 all-gather of B's bucket fused into the kernel.
+at::Tensor gemm_ag(const at::Tensor& A, const at::Tensor& B, std::vector<int64_t> peer_ptrs, at::Tensor& local_flat, const at::Tensor& segs,
+                   int64_t nseg, int64_t n_b_segs, int64_t total_tiles, int64_t shard_ready_ptr, int64_t epoch, at::Tensor& done,
+                   int64_t b_tiles_per_rank, int64_t rows_per_rank, int64_t world, int64_t rank) {
+  need(is_bf16_cuda(A) && is_bf16_cuda(B) && A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "gemm_ag: A, B bf16 2-D");
+  need(A.size(1) == B.size(1), "gemm_ag: K mismatch");
+  need(done.is_cuda() && done.numel() >= 8 && done.element_size() == 4, "gemm_ag: done must be an 8-element 32-bit CUDA tensor");
+  need(is_bf16_cuda(local_flat), "gemm_ag: local flat buffer");
+  c10::cuda::CUDAGuard g(A.device());
+  auto C = at::empty({A.size(0), B.size(0)}, A.options());
+  ZtbAgArgs ag{};
+  for (size_t i = 0; i < peer_ptrs.size() && i < 8; ++i) ag.peer[i] = reinterpret_cast<const void*>(peer_ptrs[i]);
+  ag.local = local_flat.data_ptr();
+  ag.segs = reinterpret_cast<const ZtbSegment*>(segs.data_ptr()); ag.nseg = (int)nseg; ag.n_b_segs = (int)n_b_segs; ag.total_tiles = total_tiles;
+  ag.shard_ready = reinterpret_cast<const int*>(shard_ready_ptr); ag.epoch = (int)epoch;
+  ag.done = reinterpret_cast<unsigned int*>(done.data_ptr()); ag.b_tiles_per_rank = (unsigned)b_tiles_per_rank;
+  ag.rows_per_rank = (int)rows_per_rank; ag.world = (int)world; ag.rank = (int)rank;
+  ZtbGemmArgs a{};
+  a.A = A.data_ptr(); a.B = B.data_ptr(); a.C = C.data_ptr();
+  a.M = A.size(0); a.K = A.size(1); a.N = B.size(0);
+  a.lda = A.stride(0); a.ldb = B.stride(0); a.ldc = C.stride(0);
+  a.ag = &ag;
+  check(ztb_gemm(&a, num_sms(), stream()), "gemm_ag");
+  return C;
+}
+
 // Fused (reduce-scatter +) AdamW over this rank's segments.  grad_ptrs: device addresses of every
 // peer's flat gradient buffer (first = local).  segs: uint8 CUDA tensor of packed ZtbSegment.
 void adamw_shard(at::Tensor& master, at::Tensor& m, at::Tensor& v, at::Tensor& flat_param, std::vector<int64_t> grad_ptrs,
@@ -266,6 +292,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, py::arg("A"), py::arg("B"), py::arg("C") = py::none(), py::arg("epilogue") = 0, py::arg("aux_in") = py::none(),
         py::arg("aux_out") = py::none(), py::arg("p") = 0.0, py::arg("rng") = py::none(), py::arg("op_id") = 0,
         py::arg("accumulate") = false, py::arg("a_mn") = false, py::arg("b_mn") = false);
+  m.def("gemm_ag", &gemm_ag);
   m.def("adamw_shard", &adamw_shard);
   m.def("segment_struct_size", &segment_struct_size);
   m.def("attention_fwd", &attention_fwd);

@@ -38,9 +38,51 @@ struct GemmParams {
   const uint64_t* rng;
   uint32_t op_id;
   int tiles_m, tiles_n, num_tiles;
+  int n_major_raster;   // AG variant: walk all M tiles of one N block before the next N block
+  int nb_shift;         // AG variant: logical N block 0 maps to this rank's own rows
 };
 
+// All-gather fused into the GEMM (ZeRO-1 parameter all-gather + first consuming GEMM).
+// B is a weight whose row chunks are owned by different ranks; warp 3 of every CTA pulls the remote
+// chunks of the whole bucket from the owners' symmetric parameter buffers over NVLink into the local
+// buffer while the tensor cores already work on the locally owned N blocks; the TMA producer acquires
+// a per-owner completion counter before it loads a B tile that contains gathered rows.
+struct AgParams {
+  const void* peer[8];          // flat bf16 parameter buffer of every rank (peer-mapped), index = rank
+  bf16* local;                  // this rank's flat parameter buffer
+  const ZtbSegment* segs;       // pull list: flat_off, len, decay = source rank, tile_begin; B's segments first
+  int nseg;
+  int n_b_segs;                 // the first n_b_segs segments are B's chunks (one per remote rank)
+  long long total_tiles;
+  const int* shard_ready;       // my flag row: [rank] >= epoch once that rank's chunk is final
+  int epoch;
+  unsigned int* done;           // [8] per-owner count of finished B tiles (zeroed before launch)
+  unsigned int b_tiles_per_rank;
+  int rows_per_rank;            // B rows owned by each rank
+  int world, rank;
+};
+
+constexpr int AG_TILE = 8192;   // elements per gather tile (16 KB) -- matches COPY_TILE
+
+ZTB_DEVINL unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+ZTB_DEVINL int ld_acquire_sys_s32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 ZTB_DEVINL void decode_tile(int t, const GemmParams& p, int& mb, int& nb) {
+  if (p.n_major_raster) {
+    int nl = t / p.tiles_m;
+    mb = t % p.tiles_m;
+    nb = nl + p.nb_shift;
+    if (nb >= p.tiles_n) nb -= p.tiles_n;
+    return;
+  }
   int per_group = GROUP_M * p.tiles_n;
   int g = t / per_group, r = t % per_group;
   int gm = min(GROUP_M, p.tiles_m - g * GROUP_M);
@@ -48,11 +90,11 @@ ZTB_DEVINL void decode_tile(int t, const GemmParams& p, int& mb, int& nb) {
   nb = r / gm;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool AG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
-                    const GemmParams p) {
+                    const GemmParams p, const __grid_constant__ AgParams ag) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
@@ -89,6 +131,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         int mb, nb; decode_tile(t, p, mb, nb);
+        if constexpr (AG) {
+          // rows [nb*BN, nb*BN+BN) of B: every owner other than this rank must have been gathered
+          const int r0 = (nb * BN) / ag.rows_per_rank;
+          int r1 = (nb * BN + BN - 1) / ag.rows_per_rank;
+          if (r1 >= ag.world) r1 = ag.world - 1;
+          for (int o = r0; o <= r1; ++o)
+            if (o != ag.rank)
+              while (ld_acquire_gpu_u32(ag.done + o) < ag.b_tiles_per_rank) __nanosleep(32);
+          fence_proxy_async_all();  // generic-proxy stores of the gather warps -> async-proxy TMA reads
+        }
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE_BYTES);
@@ -138,6 +190,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (AG && warp == 3) {
+    // ===================================================== all-gather warp (NVLink peer pulls)
+    if constexpr (AG) {
+      unsigned seen = 1u << ag.rank;
+      for (long long t = blockIdx.x; t < ag.total_tiles; t += gridDim.x) {
+        int lo = 0, hi = ag.nseg - 1;
+        while (lo < hi) {
+          int mid = (lo + hi + 1) >> 1;
+          if (ag.segs[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
+        }
+        const ZtbSegment sg = ag.segs[lo];
+        const int src = sg.decay;
+        if (!((seen >> src) & 1u)) {   // the owner has published this step's chunk?
+          if (lane == 0) while (ld_acquire_sys_s32(ag.shard_ready + src) < ag.epoch) __nanosleep(64);
+          __syncwarp();
+          seen |= 1u << src;
+        }
+        const bf16* sp = reinterpret_cast<const bf16*>(ag.peer[src]) + sg.flat_off;
+        bf16* dp = ag.local + sg.flat_off;
+        const long long base = (t - sg.tile_begin) * AG_TILE;
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {       // 4 x (8 x 32 lanes x 16 B) = 16 KB
+          uint4 v[8];
+          long long e[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            e[k] = base + ((long long)(it * 8 + k) * 32 + lane) * 8;
+            if (e[k] < sg.len) v[k] = ld_nc_v4(sp + e[k]);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (e[k] < sg.len) st_v4(dp + e[k], v[k]);
+        }
+        if (lo < ag.n_b_segs) {                // a tile of B: publish it to the TMA producers
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) atomicAdd(ag.done + src, 1u);
+        }
       }
     }
   } else if (warp >= 4) {
@@ -312,16 +404,18 @@ int ztb_make_tmap_2d(CUtensorMap* tm, const void* ptr, int elem_bytes, long long
   return 0;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool AG = false>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& x, const GemmParams& p,
-                  int grid, cudaStream_t st) {
-  auto kern = gemm_tcgen05_kernel<A_MN, B_MN>;
+                  int grid, cudaStream_t st, const AgParams* agp = nullptr) {
+  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, AG>;
+  AgParams ag{};
+  if (agp) ag = *agp;
   static bool configured = false;
   if (!configured) {
     ZTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
     configured = true;
   }
-  kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, b, c, x, p);
+  kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, b, c, x, p, ag);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -361,7 +455,25 @@ int ztb_gemm(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
   p.p = g->p; p.inv_keep = g->p < 1.f ? 1.f / (1.f - g->p) : 0.f;
   p.rng = g->rng; p.op_id = g->op_id;
   p.tiles_m = (g->M + BM - 1) / BM; p.tiles_n = (g->N + BN - 1) / BN; p.num_tiles = p.tiles_m * p.tiles_n;
+  p.n_major_raster = 0; p.nb_shift = 0;
   int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  if (g->ag) {
+    const ZtbAgArgs* a = g->ag;
+    if (g->a_mn_major || g->b_mn_major || g->epilogue != ZTB_EPI_NONE || g->accumulate) {
+      ztb_set_error("ztb_gemm", "all-gather fusion is implemented for the plain K-major forward GEMM", __FILE__, __LINE__);
+      return -1;
+    }
+    AgParams ag{};
+    for (int i = 0; i < 8; ++i) ag.peer[i] = i < a->world ? a->peer[i] : nullptr;
+    ag.local = (bf16*)a->local; ag.segs = a->segs; ag.nseg = a->nseg; ag.n_b_segs = a->n_b_segs; ag.total_tiles = a->total_tiles;
+    ag.shard_ready = a->shard_ready; ag.epoch = a->epoch; ag.done = a->done; ag.b_tiles_per_rank = a->b_tiles_per_rank;
+    ag.rows_per_rank = a->rows_per_rank; ag.world = a->world; ag.rank = a->rank;
+    ZTB_CUDA_CHECK(cudaMemsetAsync(a->done, 0, 8 * sizeof(unsigned), st));
+    p.n_major_raster = 1;
+    p.nb_shift = ((a->rank * a->rows_per_rank) / BN) % p.tiles_n;
+    grid = sms;  // every SM contributes a gather warp even if there are fewer tiles than SMs
+    return launch<false, false, true>(ta, tb, tc, tx, p, grid, st, &ag);
+  }
   if (g->a_mn_major && g->b_mn_major) return launch<true, true>(ta, tb, tc, tx, p, grid, st);
   if (g->a_mn_major) return launch<true, false>(ta, tb, tc, tx, p, grid, st);
   if (g->b_mn_major) return launch<false, true>(ta, tb, tc, tx, p, grid, st);

@@ -41,6 +41,12 @@ int ztb_adamw_shard(float* master, float* m, float* v, void* flat_param, const v
 
 // ---- gemm_tcgen05.cu
 enum ZtbEpilogue { ZTB_EPI_NONE = 0, ZTB_EPI_GELU = 1, ZTB_EPI_DROPOUT_ADD = 2, ZTB_EPI_GELU_BWD = 3 };
+struct ZtbAgArgs {              // all-gather fused into the GEMM (see AgParams in gemm_tcgen05.cu)
+  const void* peer[8]; void* local;
+  const ZtbSegment* segs; int nseg; int n_b_segs; long long total_tiles;
+  const int* shard_ready; int epoch;
+  unsigned int* done; unsigned int b_tiles_per_rank; int rows_per_rank; int world, rank;
+};
 struct ZtbGemmArgs {
   const void* A; const void* B; void* C;   // C[M,N] = A[M,K] * B[N,K]^T  (bf16, K contiguous in both)
   int M, N, K;
@@ -54,6 +60,7 @@ struct ZtbGemmArgs {
   int accumulate;                           // C += result (fp32 C when c_is_fp32)
   int c_is_fp32;
   int a_mn_major, b_mn_major;               // operand stored with M (resp. N) contiguous: A[K,M] / B[K,N]
+  const ZtbAgArgs* ag;                      // non-null: gather B's remote row chunks inside the kernel
 };
 int ztb_gemm(const ZtbGemmArgs* args, int sms, cudaStream_t st);
 

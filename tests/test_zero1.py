@@ -30,7 +30,9 @@ def test_layout_chunks_cover_everything():
     shapes = [("wte.weight", (128, 64)), ("blocks.0.ln1.weight", (64,)), ("blocks.0.attn.qkv.weight", (192, 64)),
               ("blocks.1.ln1.weight", (64,)), ("ln_f.weight", (70,))]
     L = FlatLayout(shapes, {}, world=4)
-    assert [b.name for b in L.buckets] == ["embed", "block0", "block1"]
+    # LayerNorm scales ride with the embed bucket; a block bucket holds the block's matrices
+    assert [b.name for b in L.buckets] == ["embed", "block0"]
+    assert [r.name for r in L.buckets[1].regions] == ["blocks.0.attn.qkv.weight"]
     assert L.total == L.shard_total * 4
     covered = torch.zeros(L.total)
     for r in L.regions:

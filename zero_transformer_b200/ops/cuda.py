@@ -124,6 +124,13 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, **kw) -> torch.Tensor:
 
 def _mm_fwd(x2: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     M, K = x2.shape
+    ag = getattr(w, "_ztb_ag", None)
+    if ag is not None and ag.pending():
+        # this weight's ZeRO-1 bucket has not been all-gathered yet: gather it inside this GEMM
+        if _tc_ok(M, w.shape[0], K) and x2.is_contiguous():
+            LAUNCHES.count += 1
+            return ag.gemm(x2, w)
+        ag.fallback()
     if _tc_ok(M, w.shape[0], K):
         return _C.gemm(x2, w)
     return x2 @ w.t()

@@ -111,6 +111,10 @@ class FusedComm:
             t, tiles = pack_segments(pl, device, COPY_TILE)
             self.pull.append((t, len(pl), tiles))
         self.grad_ptrs = self._grad.ptrs[rank:] + self._grad.ptrs[:rank]  # local copy first
+        # all-gather fused into the bucket's first GEMM: pull list with that weight's chunks first
+        self.ag_lists = {}
+        self.ag_done = torch.zeros(8, dtype=torch.int32, device=device)
+        self._ag_pending = [False] * self.nb
         self.epoch = 0
         self.stream = torch.cuda.Stream(device)
         self.ready = [torch.cuda.Event() for _ in range(self.nb)]       # bucket b usable by compute
@@ -153,20 +157,64 @@ class FusedComm:
                 self.ready[b].record(self.stream)
         self._pending[b] = True
 
-    def prefetch_all(self) -> None:
-        """Queue the all-gather of every bucket (forward order) behind the updates."""
+    def prefetch_all(self, fused_buckets=()) -> None:
+        """Queue the standalone all-gather (forward order) behind the updates for every bucket that
+        is not gathered inside its first GEMM (``fused_buckets``)."""
         if self.world == 1:
             return
         e = self.epoch
+        for b in fused_buckets:
+            self._ag_pending[b] = True
         with torch.cuda.stream(self.stream):
             for b in range(self.nb):
+                if b in fused_buckets:
+                    continue
                 self._C.wait_flags(self._my_row(FLAG_SHARD_READY, b), self.world, e)
                 segs, n, tiles = self.pull[b]
                 self._C.allgather_pull(self.flat_param, self._param.ptrs, segs, n, tiles, 0, 0)
                 self.ready[b].record(self.stream)
 
+    def ag_plan(self, b: int, first_region: str):
+        """Pull list for bucket ``b`` with ``first_region``'s chunks leading (those gate the GEMM)."""
+        key = (b, first_region)
+        if key not in self.ag_lists:
+            regs = self.layout.buckets[b].regions
+            lead = [r for r in regs if r.name == first_region]
+            rest = [r for r in regs if r.name != first_region]
+            assert len(lead) == 1
+            r0 = lead[0]
+            pl = [(r0.offset + p * r0.chunk, 0, r0.chunk, p) for p in range(self.world) if p != self.rank]
+            n_b = len(pl)
+            pl += [(r.offset + p * r.chunk, 0, r.chunk, p) for p in range(self.world) if p != self.rank for r in rest]
+            segs, tiles = pack_segments(pl, self.device, COPY_TILE)
+            k = r0.shape[1]
+            ok = r0.padded == r0.numel and (r0.chunk % k == 0)
+            self.ag_lists[key] = dict(segs=segs, nseg=len(pl), n_b=n_b, tiles=tiles, b_tiles=(r0.chunk + COPY_TILE - 1) // COPY_TILE,
+                                      rows_per_rank=r0.chunk // k, ok=ok)
+        return self.ag_lists[key]
+
+    def gemm_ag(self, b: int, first_region: str, x2: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        """``x2 @ w.T`` where ``w`` is bucket ``b``'s first-consumed weight: the bucket's all-gather
+        runs inside the GEMM kernel (compute stream); marks the bucket as gathered."""
+        plan = self.ag_plan(b, first_region)
+        out = self._C.gemm_ag(x2, w, self._param.ptrs, self.flat_param, plan["segs"], plan["nseg"], plan["n_b"], plan["tiles"],
+                              self._my_row(FLAG_SHARD_READY, b), self.epoch, self.ag_done, plan["b_tiles"], plan["rows_per_rank"],
+                              self.world, self.rank)
+        self._ag_pending[b] = False
+        self._pending[b] = False
+        return out
+
     def wait_bucket(self, b: int) -> None:
         """Compute stream waits until bucket ``b`` holds this step's parameters."""
+        if self._ag_pending[b]:
+            # nobody ran the fused GEMM for this bucket (e.g. state access before the next forward):
+            # fall back to the standalone pull on the compute stream
+            self._ag_pending[b] = False
+            self._C.wait_flags(self._my_row(FLAG_SHARD_READY, b), self.world, self.epoch)
+            segs, n, tiles = self.pull[b]
+            self._C.allgather_pull(self.flat_param, self._param.ptrs, segs, n, tiles, 0, 0)
+            self._pending[b] = False
+            return
         if self._pending[b]:
             torch.cuda.current_stream(self.device).wait_event(self.ready[b])
             self._pending[b] = False

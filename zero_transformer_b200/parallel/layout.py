@@ -66,8 +66,11 @@ class Bucket:
 def default_bucket_of(name: str) -> str:
     """``blocks.<i>.*`` -> one bucket per block; everything else -> ``embed``."""
     parts = name.split(".")
-    if len(parts) > 2 and parts[0] == "blocks" and parts[1].isdigit():
+    if len(parts) > 2 and parts[0] == "blocks" and parts[1].isdigit() and not parts[2].startswith("ln"):
         return f"block{int(parts[1])}"
+    # embedding, final norm and every LayerNorm scale: consumed before the block's first GEMM, so they
+    # travel with the standalone all-gather at the start of the step (the per-block buckets are
+    # gathered inside their QKV GEMM)
     return "embed"
 
 

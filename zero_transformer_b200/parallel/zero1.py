@@ -133,9 +133,11 @@ class Zero1Engine:
         for b in L.buckets:
             if b.name.startswith("block"):
                 self._block_bucket[int(b.name[5:])] = b.index
+        self._ag_fused_buckets = ()
         if self._fused is not None and hasattr(model, "block_backward_done_hook"):
             model.block_backward_done_hook = self._on_block_backward_done
             model.block_forward_pre_hook = self._on_block_forward_pre
+            self._install_ag_gemm(model)
 
     # ------------------------------------------------------------------
     @property
@@ -160,8 +162,27 @@ class Zero1Engine:
 
     def _on_block_forward_pre(self, i: int) -> None:
         b = self._block_bucket.get(i)
-        if b is not None:
+        if b is not None and not self._fused._ag_pending[b]:
             self._fused.wait_bucket(b)
+
+    def _install_ag_gemm(self, model) -> None:
+        """Tag every block's QKV weight -- the first GEMM that consumes the block's bucket -- so that
+        ``ops.linear`` runs the all-gather-fused GEMM when that bucket still has to be gathered."""
+        import os
+
+        if self.world == 1 or os.environ.get("ZTB_AG_GEMM", "1") != "1":
+            return
+        fused = []
+        for i, blk in enumerate(getattr(model, "blocks", [])):
+            b = self._block_bucket.get(i)
+            name = f"blocks.{i}.attn.qkv.weight"
+            if b is None or name not in self.layout.by_name:
+                continue
+            if not self._fused.ag_plan(b, name)["ok"]:
+                continue
+            blk.attn.qkv.weight._ztb_ag = _AgHandle(self._fused, b, name)
+            fused.append(b)
+        self._ag_fused_buckets = tuple(fused)
 
     _in_engine_backward = False
 
@@ -216,7 +237,9 @@ class Zero1Engine:
                 if b not in self._updated:
                     f.bucket_update(b, **kw)
             self._updated.clear()
-            f.prefetch_all()            # all-gather, queued in forward order, overlaps the next forward
+            # all-gather: embed bucket (+ anything without a fused consumer) by the standalone P2P pull,
+            # queued now so it overlaps the tail of this step; block buckets inside their QKV GEMM
+            f.prefetch_all(fused_buckets=self._ag_fused_buckets if f.world > 1 else ())
             if self._embed_bucket is not None:
                 f.wait_bucket(self._embed_bucket)
             if not hasattr(self.model, "block_forward_pre_hook") or self.model.block_forward_pre_hook is None:
@@ -346,6 +369,22 @@ class Zero1Engine:
         return (f"ZeRO-1 rank {self.rank}/{self.world} [{self.backend}]: params {pb * gb:.2f} GiB ({self.compute_dtype}), "
                 f"grads {gbs * gb:.2f} GiB ({self.grad_dtype}), fp32 master+m+v shard {ob * gb:.2f} GiB "
                 f"(unsharded would be {ob * self.world * gb:.2f} GiB)")
+
+
+class _AgHandle:
+    """Attached to a block's QKV weight: lets the op layer run the all-gather-fused GEMM."""
+
+    def __init__(self, fused, bucket: int, region: str):
+        self.fused, self.bucket, self.region = fused, bucket, region
+
+    def pending(self) -> bool:
+        return self.fused._ag_pending[self.bucket]
+
+    def gemm(self, x2, w):
+        return self.fused.gemm_ag(self.bucket, self.region, x2, w)
+
+    def fallback(self) -> None:
+        self.fused.wait_bucket(self.bucket)
 
 
 class PlainAdamW:
