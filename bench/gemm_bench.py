@@ -36,16 +36,20 @@ def main():
         a = torch.randn(m, k, device="cuda").bfloat16()
         b = torch.randn(n, k, device="cuda").bfloat16()
         fl = 2.0 * m * n * k
-        t_tc = timeit(lambda: K._C.gemm(a, b))
+        t_tc = timeit(lambda: K._C.gemm(a, b, two_cta=False))
+        t_2 = timeit(lambda: K._C.gemm(a, b, two_cta=True))
         t_cb = timeit(lambda: a @ b.t())
         row = {"name": name, "M": m, "N": n, "K": k, "tc_ms": round(t_tc, 4), "cublas_ms": round(t_cb, 4),
-               "tc_tflops": round(fl / t_tc / 1e9, 1), "cublas_tflops": round(fl / t_cb / 1e9, 1)}
+               "tc_tflops": round(fl / t_tc / 1e9, 1), "tc2_tflops": round(fl / t_2 / 1e9, 1), "cublas_tflops": round(fl / t_cb / 1e9, 1)}
         # backward flavours
         dy = torch.randn(m, n, device="cuda").bfloat16()
-        t_dg = timeit(lambda: K._C.gemm(dy, b, b_mn=True))
+        t_dg = timeit(lambda: K._C.gemm(dy, b, b_mn=True, two_cta=False))
+        t_dg2 = timeit(lambda: K._C.gemm(dy, b, b_mn=True, two_cta=True))
+        t_wg2 = timeit(lambda: K._C.gemm(dy, a, a_mn=True, b_mn=True, two_cta=True))
         t_dg_cb = timeit(lambda: dy @ b)
-        t_wg = timeit(lambda: K._C.gemm(dy, a, a_mn=True, b_mn=True))
+        t_wg = timeit(lambda: K._C.gemm(dy, a, a_mn=True, b_mn=True, two_cta=False))
         t_wg_cb = timeit(lambda: dy.t() @ a)
+        row.update({"dgrad_tc2_tflops": round(fl / t_dg2 / 1e9, 1), "wgrad_tc2_tflops": round(fl / t_wg2 / 1e9, 1)})
         row.update({"dgrad_tc_tflops": round(fl / t_dg / 1e9, 1), "dgrad_cublas_tflops": round(fl / t_dg_cb / 1e9, 1),
                     "wgrad_tc_tflops": round(fl / t_wg / 1e9, 1), "wgrad_cublas_tflops": round(fl / t_wg_cb / 1e9, 1)})
         rows.append(row)

@@ -1,0 +1,377 @@
+// 2-CTA (cta_group::2) variant of the tcgen05 GEMM: a pair of CTAs on one TPC computes a 256x256
+// tile.  Each CTA stages 128 rows of A and 128 rows (N) of B per 64-wide K block -- 32 KB instead of
+// the 48 KB a lone 128x256 CTA needs for the same MMA work -- so the L2 -> SM traffic per FLOP drops
+// by a third and the smem ring deepens to 6 stages.  The leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' smem and writes both CTAs' TMEM;
+// completion is multicast to both CTAs' mbarriers.  Everything else (operand majors, epilogues,
+// TMEM double buffering, TMA store / reduce-add) matches gemm_tcgen05.cu.
+#include <cuda.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "launchers.h"
+
+namespace ztb {
+namespace g2 {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 6;
+constexpr int TILE_M = 256;                  // rows per CTA pair
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_STAGE_BYTES = 128 * BK * 2;  // 16 KB: this CTA's half of the 256 B rows
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int CBUF_BYTES = BM * 128;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 2 * CBUF_BYTES + 256 + 1024;
+constexpr int GEMM_THREADS = 256;
+constexpr int GROUP_M = 8;                   // in 256-row tiles
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
+
+struct GemmParams {
+  int M, N, K;
+  int epi, c_fp32, accumulate;
+  const bf16* aux_in;
+  long long ld_aux;
+  int has_aux_out;
+  float p, inv_keep;
+  const uint64_t* rng;
+  uint32_t op_id;
+  int tiles_m, tiles_n, num_tiles;
+};
+
+ZTB_DEVINL void decode_tile(int t, const GemmParams& p, int& mb, int& nb) {
+  int per_group = GROUP_M * p.tiles_n;
+  int g = t / per_group, r = t % per_group;
+  int gm = min(GROUP_M, p.tiles_m - g * GROUP_M);
+  mb = g * GROUP_M + r % gm;
+  nb = r / gm;
+}
+
+ZTB_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+ZTB_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+ZTB_DEVINL void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint64_t* leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(leader_bar) & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+ZTB_DEVINL void umma_f16_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+ZTB_DEVINL void umma_commit_2sm(uint64_t* bar) {  // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+ZTB_DEVINL void mbar_arrive_cta0(uint64_t* bar) {  // arrive on CTA 0's copy of `bar`
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(bar)));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
+                     const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + STAGES * A_STAGE_BYTES;
+  uint8_t* smC = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smC + 2 * CBUF_BYTES);
+  uint64_t* full = bars;                     // [STAGES]  leader's copy collects both CTAs' TMA bytes
+  uint64_t* empty = bars + STAGES;           // [STAGES]  multicast commit -> both CTAs
+  uint64_t* tfull = bars + 2 * STAGES;       // [2]       multicast commit -> both CTAs
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]       leader's copy: 8 epilogue warps (both CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int kblocks = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmC);
+    if (p.has_aux_out) prefetch_tmap(&tmAux);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = pair; t < p.num_tiles; t += num_pairs) {
+        int mb, nb; decode_tile(t, p, mb, nb);
+        const int m0 = mb * TILE_M + cta_rank * BM;        // this CTA's A rows
+        const int nrow0 = nb * BN + cta_rank * 128;        // this CTA's B rows
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
+          uint8_t* a = smA + stage * A_STAGE_BYTES;
+          uint8_t* b = smB + stage * B_STAGE_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_2d_2sm(a, &tmA, &full[stage], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(a + j * 8192, &tmA, &full[stage], m0 + j * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_2sm(b, &tmB, &full[stage], kb * BK, nrow0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(b + j * 8192, &tmB, &full[stage], nrow0 + j * 64, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA, single thread)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = pair; t < p.num_tiles; t += num_pairs) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smA + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(smB + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            uint64_t da = A_MN ? make_smem_desc(a_addr + k * 2048, 8192, 1024, kSwizzle128B)
+                               : make_smem_desc(a_addr + k * 32, 16, 1024, kSwizzle128B);
+            uint64_t db = B_MN ? make_smem_desc(b_addr + k * 2048, 8192, 1024, kSwizzle128B)
+                               : make_smem_desc(b_addr + k * 32, 16, 1024, kSwizzle128B);
+            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty[stage]);
+          if (kb == kblocks - 1) umma_commit_2sm(&tfull[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (4 warps per CTA, its 128 rows)
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    const int etid = threadIdx.x - 128;
+    const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+    const uint32_t thr = dropout_threshold(p.p);
+    uint64_t seed = 0, stream = 0;
+    if (p.epi == ZTB_EPI_DROPOUT_ADD) { seed = p.rng[0]; stream = p.rng[1] * 65536ull + p.op_id; }
+    Philox ph(seed);
+    auto arrive_tempty = [&](int a) { if (leader) mbar_arrive(&tempty[a]); else mbar_arrive_cta0(&tempty[a]); };
+    int acc = 0; uint32_t acc_phase = 0;
+    int cbuf = 0;
+    for (int t = pair; t < p.num_tiles; t += num_pairs) {
+      int mb, nb; decode_tile(t, p, mb, nb);
+      const int m0 = mb * TILE_M + cta_rank * BM, n0 = nb * BN;
+      const int grow = m0 + row;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_acc = tmem_base + lane_addr + acc * BN;
+      // One staging buffer holds 128 B per row: 64 bf16 columns or 32 fp32 columns.  Buffers
+      // alternate; before overwriting one, the issuing thread waits until at most one bulk store
+      // (the other buffer's) is still reading smem.
+      auto begin_buffer = [&]() {
+        if (etid == 0) tma_wait_group_read<1>();
+        named_bar_sync(1, 128);
+      };
+      auto end_buffer = [&](const CUtensorMap* tm, int col) {
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (etid == 0) {
+          if (p.accumulate) tma_reduce_add_2d(tm, smC + cbuf * CBUF_BYTES, col, m0);
+          else tma_store_2d(tm, smC + cbuf * CBUF_BYTES, col, m0);
+          tma_commit_group();
+        }
+        cbuf ^= 1;
+      };
+      auto stage_bf16 = [&](const float* v) {  // 64 values -> this thread's swizzled 128-byte row
+        uint8_t* rowp = smC + cbuf * CBUF_BYTES + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 o = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                               pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
+        }
+      };
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        uint32_t r[64];
+        tmem_ld_32x32b_x32(t_acc + c * 64, r);
+        tmem_ld_32x32b_x32(t_acc + c * 64 + 32, r + 32);
+        tmem_wait_ld();
+        if (c == BN / 64 - 1) {  // last TMEM read of this accumulator: hand it back to the MMA warp
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) arrive_tempty(acc);
+        }
+        const int gcol = n0 + c * 64;
+        float v[64];
+#pragma unroll
+        for (int k = 0; k < 64; ++k) v[k] = __uint_as_float(r[k]);
+        if (p.epi == ZTB_EPI_GELU) {
+          if (p.has_aux_out) {  // pre-activation Z leaves through its own tensor map
+            begin_buffer();
+            stage_bf16(v);
+            end_buffer(&tmAux, gcol);
+          }
+#pragma unroll
+          for (int k = 0; k < 64; ++k) v[k] = gelu_tanh(v[k]);
+        } else if (p.epi == ZTB_EPI_DROPOUT_ADD || p.epi == ZTB_EPI_GELU_BWD) {
+          const bool in_rows = grow < p.M;
+          const bf16* ap = p.aux_in + (size_t)grow * p.ld_aux + gcol;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (in_rows && gcol + q * 8 < p.N) u = ld_nc_v4(ap + q * 8);
+            uint32_t us[4] = {u.x, u.y, u.z, u.w};
+            if (p.epi == ZTB_EPI_DROPOUT_ADD) {
+              size_t idx = (size_t)grow * p.N + gcol + q * 8;
+              uint4 r0 = ph(idx >> 2, stream), r1 = ph((idx >> 2) + 1, stream);
+              uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float2 rf = unpack_bf16(us[k]);
+                float a = rr[2 * k] >= thr ? v[q * 8 + 2 * k] * p.inv_keep : 0.f;
+                float b = rr[2 * k + 1] >= thr ? v[q * 8 + 2 * k + 1] * p.inv_keep : 0.f;
+                v[q * 8 + 2 * k] = rf.x + a;
+                v[q * 8 + 2 * k + 1] = rf.y + b;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float2 zf = unpack_bf16(us[k]);
+                v[q * 8 + 2 * k] *= gelu_tanh_grad(zf.x);
+                v[q * 8 + 2 * k + 1] *= gelu_tanh_grad(zf.y);
+              }
+            }
+          }
+        }
+        if (p.c_fp32) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            begin_buffer();
+            uint8_t* rowp = smC + cbuf * CBUF_BYTES + row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float* s4 = v + h * 32 + 4 * j;
+              uint4 o = make_uint4(__float_as_uint(s4[0]), __float_as_uint(s4[1]), __float_as_uint(s4[2]), __float_as_uint(s4[3]));
+              *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
+            }
+            end_buffer(&tmC, gcol + h * 32);
+          }
+        } else {
+          begin_buffer();
+          stage_bf16(v);
+          end_buffer(&tmC, gcol);
+        }
+      }
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+    if (etid == 0) tma_wait_group<0>();
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();   // nobody may exit (or free TMEM) while the peer still reads this CTA's smem / barriers
+  if (warp == 2) {
+    tc_fence_after_sync();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+}  // namespace g2
+}  // namespace ztb
+
+using namespace ztb;
+
+int ztb_make_tmap_2d(CUtensorMap* tm, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
+                     int box_cols, int box_rows);
+
+template <bool A_MN, bool B_MN>
+static int launch2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& x, const g2::GemmParams& p,
+                   int grid, cudaStream_t st) {
+  auto kern = g2::gemm2_tcgen05_kernel<A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    ZTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g2::GEMM_SMEM));
+    configured = true;
+  }
+  kern<<<grid, g2::GEMM_THREADS, g2::GEMM_SMEM, st>>>(a, b, c, x, p);  // cluster dims are compile-time (2,1,1)
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// Same contract as ztb_gemm (without the all-gather variant); M is processed in 256-row tiles.
+int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
+  using namespace g2;
+  if (g->M <= 0 || g->N <= 0 || g->K <= 0) return 0;
+  if ((g->lda % 8) || (g->ldb % 8) || (g->ldc % (g->c_is_fp32 ? 4 : 8)) || (g->K % 8) || (g->N % 8)) {
+    ztb_set_error("ztb_gemm_2cta", "leading dimensions / K / N must be multiples of 8 elements", __FILE__, __LINE__);
+    return -1;
+  }
+  CUtensorMap ta, tb, tc, tx;
+  int rc;
+  rc = g->a_mn_major ? ztb_make_tmap_2d(&ta, g->A, 2, g->K, g->M, g->lda, 64, 64)
+                     : ztb_make_tmap_2d(&ta, g->A, 2, g->M, g->K, g->lda, BK, BM);
+  if (rc) return rc;
+  rc = g->b_mn_major ? ztb_make_tmap_2d(&tb, g->B, 2, g->K, g->N, g->ldb, 64, 64)
+                     : ztb_make_tmap_2d(&tb, g->B, 2, g->N, g->K, g->ldb, BK, 128);
+  if (rc) return rc;
+  rc = g->c_is_fp32 ? ztb_make_tmap_2d(&tc, g->C, 4, g->M, g->N, g->ldc, 32, BM)
+                    : ztb_make_tmap_2d(&tc, g->C, 2, g->M, g->N, g->ldc, 64, BM);
+  if (rc) return rc;
+  tx = tc;
+  GemmParams p;
+  p.M = g->M; p.N = g->N; p.K = g->K;
+  p.epi = g->epilogue; p.c_fp32 = g->c_is_fp32; p.accumulate = g->accumulate;
+  p.aux_in = (const bf16*)g->aux_in; p.ld_aux = g->ld_aux;
+  p.has_aux_out = (g->epilogue == ZTB_EPI_GELU && g->aux_out != nullptr) ? 1 : 0;
+  if (p.has_aux_out) {
+    if (g->c_is_fp32 || g->accumulate) { ztb_set_error("ztb_gemm_2cta", "GELU epilogue needs a bf16 non-accumulating C", __FILE__, __LINE__); return -1; }
+    rc = ztb_make_tmap_2d(&tx, g->aux_out, 2, g->M, g->N, g->ld_aux, 64, BM);
+    if (rc) return rc;
+  }
+  if ((g->epilogue == ZTB_EPI_DROPOUT_ADD || g->epilogue == ZTB_EPI_GELU_BWD) && g->aux_in == nullptr) {
+    ztb_set_error("ztb_gemm_2cta", "epilogue needs aux_in", __FILE__, __LINE__); return -1;
+  }
+  p.p = g->p; p.inv_keep = g->p < 1.f ? 1.f / (1.f - g->p) : 0.f;
+  p.rng = g->rng; p.op_id = g->op_id;
+  p.tiles_m = (g->M + TILE_M - 1) / TILE_M; p.tiles_n = (g->N + BN - 1) / BN; p.num_tiles = p.tiles_m * p.tiles_n;
+  int pairs = sms / 2;
+  if (p.num_tiles < pairs) pairs = p.num_tiles;
+  int grid = pairs * 2;
+  if (g->a_mn_major && g->b_mn_major) return launch2<true, true>(ta, tb, tc, tx, p, grid, st);
+  if (g->a_mn_major) return launch2<true, false>(ta, tb, tc, tx, p, grid, st);
+  if (g->b_mn_major) return launch2<false, true>(ta, tb, tc, tx, p, grid, st);
+  return launch2<false, false>(ta, tb, tc, tx, p, grid, st);
+}

@@ -61,7 +61,9 @@ struct ZtbGemmArgs {
   int c_is_fp32;
   int a_mn_major, b_mn_major;               // operand stored with M (resp. N) contiguous: A[K,M] / B[K,N]
   const ZtbAgArgs* ag;                      // non-null: gather B's remote row chunks inside the kernel
+  int two_cta;                              // use the cta_group::2 (256x256 per CTA pair) kernel
 };
+int ztb_gemm_2cta(const ZtbGemmArgs* args, int sms, cudaStream_t st);
 int ztb_gemm(const ZtbGemmArgs* args, int sms, cudaStream_t st);
 
 // ---- comm.cu (NVLink peer-memory kernels; all pointers are device addresses, peers mapped via symmetric memory)

@@ -28,23 +28,25 @@ GEMM_SHAPES = [(256, 256, 64), (128, 256, 128), (512, 512, 512), (1024, 2048, 20
                (4096, 6144, 2048), (2048, 2048, 8192), (256, 50304, 1024)]
 
 
+@pytest.mark.parametrize("two_cta", [False, True])
 @pytest.mark.parametrize("M,N,K_", GEMM_SHAPES)
-def test_gemm_nt(K, M, N, K_):
+def test_gemm_nt(K, M, N, K_, two_cta):
     a, b = _rand(M, K_), _rand(N, K_)
-    c = K._C.gemm(a, b)
+    c = K._C.gemm(a, b, two_cta=two_cta)
     ref = a.float() @ b.float().t()
     _close(c, ref, rtol=2e-2, atol=2e-2 * math.sqrt(K_))
 
 
 @pytest.mark.parametrize("M,N,K_", [(256, 256, 64), (512, 768, 384), (1024, 2048, 4096), (200, 264, 72)])
+@pytest.mark.parametrize("two_cta", [False, True])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
-def test_gemm_mn_major(K, M, N, K_, a_mn, b_mn):
+def test_gemm_mn_major(K, M, N, K_, a_mn, b_mn, two_cta):
     if a_mn and M % 8:
         pytest.skip("MN-major A needs M % 8 == 0 (TMA stride)")
     a, b = _rand(M, K_), _rand(N, K_)
     A = a.t().contiguous() if a_mn else a  # stored [K, M]
     B = b.t().contiguous() if b_mn else b  # stored [K, N]
-    c = K._C.gemm(A, B, a_mn=a_mn, b_mn=b_mn)
+    c = K._C.gemm(A, B, a_mn=a_mn, b_mn=b_mn, two_cta=two_cta)
     _close(c, a.float() @ b.float().t(), rtol=2e-2, atol=2e-2 * math.sqrt(K_))
 
 
@@ -284,3 +286,23 @@ def test_attention_dropout_fwd_bwd_consistent(K):
         o0 = alibi_attention((qkv.float() - d).bfloat16(), None, H, hd ** -0.5, 0.2).float()
     fd = ((o1 - o0) * dout.float()).sum().item() / 2
     assert abs(fd - lin) < 0.08 * max(abs(lin), abs(fd), 1.0), (fd, lin)
+
+
+def test_gemm_2cta_epilogues(K):
+    M, N, Kd = 512, 1024, 512
+    a, b, res = _rand(M, Kd, scale=0.5), _rand(N, Kd, scale=0.05), _rand(M, N)
+    rng = K.rng_state("cuda")
+    z1 = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    z2 = torch.empty_like(z1)
+    g1 = K._C.gemm(a, b, epilogue=K.EPI_GELU, aux_out=z1, two_cta=False)
+    g2 = K._C.gemm(a, b, epilogue=K.EPI_GELU, aux_out=z2, two_cta=True)
+    assert torch.equal(g1, g2) and torch.equal(z1, z2)
+    d1 = K._C.gemm(a, b, epilogue=K.EPI_DROPOUT_ADD, aux_in=res, p=0.25, rng=rng, op_id=5, two_cta=False)
+    d2 = K._C.gemm(a, b, epilogue=K.EPI_DROPOUT_ADD, aux_in=res, p=0.25, rng=rng, op_id=5, two_cta=True)
+    assert torch.equal(d1, d2)
+    dy, x = _rand(1024, 512), _rand(1024, 256)
+    c1 = torch.zeros(512, 256, device="cuda")
+    c2 = torch.zeros(512, 256, device="cuda")
+    K._C.gemm(dy, x, C=c1, accumulate=True, a_mn=True, b_mn=True, two_cta=False)
+    K._C.gemm(dy, x, C=c2, accumulate=True, a_mn=True, b_mn=True, two_cta=True)
+    torch.testing.assert_close(c1, c2, rtol=1e-5, atol=1e-3)

@@ -16,7 +16,7 @@ _ROOT = os.path.dirname(_PKG)
 CSRC = os.path.join(_ROOT, "csrc")
 EXT_DIR = os.path.join(_PKG, "_ext")
 NAME = "_ztb_cuda"
-SOURCES = ["bindings.cpp", "host_util.cu", "elementwise.cu", "optim.cu", "gemm_tcgen05.cu", "attention.cu", "comm.cu"]
+SOURCES = ["bindings.cpp", "host_util.cu", "elementwise.cu", "optim.cu", "gemm_tcgen05.cu", "gemm2_tcgen05.cu", "attention.cu", "comm.cu"]
 CUDA_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

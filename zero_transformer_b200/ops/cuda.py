@@ -47,10 +47,19 @@ class _Counting:
         fn = getattr(self._mod, name)
         if not callable(fn):
             return fn
-
-        def wrapped(*a, **k):
-            LAUNCHES.count += 1
-            return fn(*a, **k)
+        if name == "gemm":
+            def wrapped(*a, **k):
+                LAUNCHES.count += 1
+                if "two_cta" not in k and CONFIG.gemm_2cta:
+                    # measured on B200: the CTA-pair kernel wins everywhere except the vocabulary-sized
+                    # GEMMs (N or K = 50304), where the 1-CTA raster keeps more of wte in L2
+                    big = max(a[0].shape[0], a[0].shape[1], a[1].shape[0], a[1].shape[1]) > 20000
+                    k["two_cta"] = not big
+                return fn(*a, **k)
+        else:
+            def wrapped(*a, **k):
+                LAUNCHES.count += 1
+                return fn(*a, **k)
 
         setattr(self, name, wrapped)
         return wrapped
@@ -66,6 +75,7 @@ class _Config:
     tc_gemm = os.environ.get("ZTB_TC_GEMM", "1") == "1"          # tcgen05 GEMM (0 -> cuBLAS everywhere)
     tc_gemm_bwd = os.environ.get("ZTB_TC_GEMM_BWD", "1") == "1"  # MN-major dgrad/wgrad on tcgen05
     fuse_wgrad = os.environ.get("ZTB_FUSE_WGRAD", "1") == "1"    # accumulate dW into param.grad in the epilogue
+    gemm_2cta = os.environ.get("ZTB_GEMM_2CTA", "1") == "1"      # cta_group::2 256x256 kernel for the big GEMMs
     attn_impl = os.environ.get("ZTB_ATTN", "auto")                # auto | tc (own kernel) | flash (flash_attn library) | ref
 
 
