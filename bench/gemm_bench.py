@@ -54,6 +54,24 @@ def main():
                     "wgrad_tc_tflops": round(fl / t_wg / 1e9, 1), "wgrad_cublas_tflops": round(fl / t_wg_cb / 1e9, 1)})
         rows.append(row)
         print(json.dumps(row), flush=True)
+    # fused-epilogue variants at the fc shapes
+    m, d = M, 2048
+    x = torch.randn(m, d, device="cuda").bfloat16()
+    w1 = torch.randn(4 * d, d, device="cuda").bfloat16() * 0.02
+    w2 = torch.randn(d, 4 * d, device="cuda").bfloat16() * 0.02
+    z = torch.randn(m, 4 * d, device="cuda").bfloat16()
+    dy = torch.randn(m, d, device="cuda").bfloat16()
+    res = torch.randn(m, d, device="cuda").bfloat16()
+    rng = K.rng_state("cuda")
+    fl = 2.0 * m * d * 4 * d
+    for two in (False, True):
+        r = {"two_cta": two}
+        r["fc_in_gelu"] = round(fl / timeit(lambda: K._C.gemm(x, w1, epilogue=K.EPI_GELU, aux_out=z, two_cta=two)) / 1e9, 1)
+        r["fc_out_dropout_add"] = round(fl / timeit(lambda: K._C.gemm(z, w2, epilogue=K.EPI_DROPOUT_ADD, aux_in=res, p=0.1, rng=rng, op_id=1, two_cta=two)) / 1e9, 1)
+        r["fc_out_plain"] = round(fl / timeit(lambda: K._C.gemm(z, w2, two_cta=two)) / 1e9, 1)
+        r["dgrad_gelu_bwd"] = round(fl / timeit(lambda: K._C.gemm(dy, w2, epilogue=K.EPI_GELU_BWD, aux_in=z, b_mn=True, two_cta=two)) / 1e9, 1)
+        r["dgrad_plain"] = round(fl / timeit(lambda: K._C.gemm(dy, w2, b_mn=True, two_cta=two)) / 1e9, 1)
+        print(json.dumps(r), flush=True)
     return rows
 
 
