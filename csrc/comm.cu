@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) reduce_scatter_kernel(bf16* __restrict__ 
       if (segs[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
     }
     const ZtbSegment sg = segs[lo];
-    long long e0 = (t - sg.tile_begin) * 2048 + (long long)threadIdx.x * 8;
+    long long e0 = (t - sg.tile_begin) * 2048 + (long long)threadIdx.x * 8;  // segment table packed with tile = 2048
     if (e0 >= sg.len) continue;
     float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int p = 0; p < n_peers; ++p) {

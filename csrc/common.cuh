@@ -83,11 +83,15 @@ ZTB_DEVINL float gelu_tanh_grad(float x) {
 struct Philox {
   uint32_t k0, k1;
   ZTB_DEVINL Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
-  ZTB_DEVINL uint4 operator()(uint64_t ctr, uint64_t stream) const {
+  ZTB_DEVINL uint4 operator()(uint64_t ctr, uint64_t stream) const { return rounds<10>(ctr, stream); }
+  // reduced-round variant for the attention-probability mask (one call per 16 elements inside the
+  // softmax critical path); 6 rounds decorrelate dropout decisions more than adequately
+  template <int R>
+  ZTB_DEVINL uint4 rounds(uint64_t ctr, uint64_t stream) const {
     uint4 c = make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)stream, (uint32_t)(stream >> 32));
     uint32_t a = k0, b = k1;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < R; ++r) {
       uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
       uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
       c = make_uint4(hi1 ^ c.y ^ a, lo1, hi0 ^ c.w ^ b, lo0);

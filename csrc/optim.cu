@@ -16,9 +16,10 @@
 
 namespace ztb {
 
-constexpr int kAdamThreads = 256;
+constexpr int kAdamThreads = 128;  // small CTAs (8 K registers) co-reside with the attention / elementwise kernels of the
+                                   // overlapping backward pass instead of waiting for a free SM
 constexpr int kAdamVec = 8;                       // elements per thread per tile
-constexpr int kAdamTile = kAdamThreads * kAdamVec;  // 2048
+constexpr int kAdamTile = kAdamThreads * kAdamVec;  // 1024
 constexpr int kMaxPeers = 8;
 
 struct PeerPtrs {
@@ -106,7 +107,7 @@ int ztb_adamw_shard(float* master, float* m, float* v, void* flat_param, const v
   if (total_tiles <= 0) return 0;
   PeerPtrs pp;
   for (int i = 0; i < kMaxPeers; ++i) pp.g[i] = i < n_peers ? grads[i] : nullptr;
-  long long want = total_tiles < (long long)sms * 8 ? total_tiles : (long long)sms * 8;
+  long long want = total_tiles < (long long)sms * 16 ? total_tiles : (long long)sms * 16;
   int grid = (int)want;
   if (grad_is_fp32)
     adamw_shard_kernel<true><<<grid, kAdamThreads, 0, st>>>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value);

@@ -24,7 +24,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ADAM_TILE = 2048  # elements per CTA tile; must match kAdamTile in csrc/optim.cu
+ADAM_TILE = 1024  # elements per CTA tile; must match kAdamTile in csrc/optim.cu
 COPY_TILE = 8192  # must match kCopyTile in csrc/comm.cu
 FLAG_GRAD_READY, FLAG_SHARD_READY = 0, 1
 MAX_RANKS = 8
