@@ -34,7 +34,7 @@ ZTB_DEVINL float ex2_ftz(float x) {
 
 template <int HD>
 struct AttnSmem {
-  static constexpr int CH = HD / 64;               // 64-column (128-byte) chunks per row
+  static constexpr int CH = (HD + 63) / 64;        // 64-column (128-byte) chunks per row (head_dim 96 is staged as 128)
   static constexpr int TILE = 128 * 128 * CH;      // bytes of a [128 x HD] bf16 tile
   static constexpr int Q_OFF = 0;
   static constexpr int K_OFF = TILE;               // 2 stages
@@ -49,6 +49,7 @@ struct AttnParams {
   float scale_log2;          // softmax scale * log2(e)
   const float* slopes;       // [H] or nullptr
   float* lse;                // [B, H, T] natural-log LSE (for backward)
+  bf16* out;                 // [B*T, H*hd] (direct stores for a partial 64-column chunk, head_dim 96)
   uint32_t drop_thr8;        // keep iff byte >= thr (0 = no dropout)
   float inv_keep;            // 1 / (1 - thr/256)
   const uint64_t* rng;
@@ -184,6 +185,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int qi = qb * ATT_BM + r;
+    constexpr int SPLIT = (HD == 64) ? 32 : 64;   // output columns: half 0 owns [0, SPLIT), half 1 [SPLIT, HD)
+    constexpr int FULLCH = HD / 64;               // 64-column chunks that leave through {64 x 128} TMA boxes
+    const int hc0 = hf ? SPLIT : 0, hcn = hf ? HD - SPLIT : SPLIT;
     const float slope2 = p.slopes ? p.slopes[h] * 1.4426950408889634f : 0.f;
     const bool use_drop = p.drop_thr8 != 0;
     uint64_t seed = 0, stream = 0;
@@ -248,9 +252,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tc_fence_after_sync();
         if (__any_sync(0xffffffffu, alpha != 1.f)) {  // this thread rescales its half of the O columns
 #pragma unroll
-          for (int c = 0; c < HD / 64; ++c) {
+          for (int c = 0; c < 2; ++c) {
+            if (c * 32 >= hcn) break;
             uint32_t o[32];
-            const uint32_t ta = tO + lane_addr + hf * (HD / 2) + c * 32;
+            const uint32_t ta = tO + lane_addr + hc0 + c * 32;
             tmem_ld_32x32b_x32(ta, o);
             tmem_wait_ld();
 #pragma unroll
@@ -275,21 +280,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     named_bar_sync(3, 256);
     l += xch[512 + (hf ^ 1) * 128 + r];
     const float inv = (use_drop ? p.inv_keep : 1.f) / l;
-    constexpr int OC = HD / 2;               // O columns per thread
 #pragma unroll
-    for (int c = 0; c < OC / 32; ++c) {
+    for (int c = 0; c < 2; ++c) {
+      if (c * 32 >= hcn) break;
       uint32_t o[32];
-      const int col = hf * OC + c * 32;      // first O column of this chunk
+      const int col = hc0 + c * 32;          // first O column of this 32-column piece
       tmem_ld_32x32b_x32(tO + lane_addr + col, o);
       tmem_wait_ld();
-      uint8_t* orow = smP + (col >> 6) * 16384 + r * 128;
+      uint4 o4[4];
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        uint4 o4 = make_uint4(pack_bf16(__uint_as_float(o[q4 * 8 + 0]) * inv, __uint_as_float(o[q4 * 8 + 1]) * inv),
-                              pack_bf16(__uint_as_float(o[q4 * 8 + 2]) * inv, __uint_as_float(o[q4 * 8 + 3]) * inv),
-                              pack_bf16(__uint_as_float(o[q4 * 8 + 4]) * inv, __uint_as_float(o[q4 * 8 + 5]) * inv),
-                              pack_bf16(__uint_as_float(o[q4 * 8 + 6]) * inv, __uint_as_float(o[q4 * 8 + 7]) * inv));
-        *reinterpret_cast<uint4*>(orow + (((((col & 63) >> 3) + q4) ^ (r & 7)) << 4)) = o4;
+      for (int q4 = 0; q4 < 4; ++q4)
+        o4[q4] = make_uint4(pack_bf16(__uint_as_float(o[q4 * 8 + 0]) * inv, __uint_as_float(o[q4 * 8 + 1]) * inv),
+                            pack_bf16(__uint_as_float(o[q4 * 8 + 2]) * inv, __uint_as_float(o[q4 * 8 + 3]) * inv),
+                            pack_bf16(__uint_as_float(o[q4 * 8 + 4]) * inv, __uint_as_float(o[q4 * 8 + 5]) * inv),
+                            pack_bf16(__uint_as_float(o[q4 * 8 + 6]) * inv, __uint_as_float(o[q4 * 8 + 7]) * inv));
+      if ((col >> 6) < FULLCH) {
+        uint8_t* orow = smP + (col >> 6) * 16384 + r * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(orow + (((((col & 63) >> 3) + q4) ^ (r & 7)) << 4)) = o4[q4];
+      } else {  // partial chunk (head_dim 96): straight to global, 64 contiguous bytes per row
+        bf16* gp = p.out + (size_t)(row0 + r) * D + colQ + col;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) st_v4(gp + q4 * 8, o4[q4]);
       }
     }
     if (hf == 0) p.lse[(size_t)bh * p.T + qi] = (m + log2f(l)) * 0.6931471805599453f;
@@ -297,7 +309,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     named_bar_sync(1, 256);
     if (threadIdx.x == 64) {
 #pragma unroll
-      for (int c = 0; c < CH; ++c) tma_store_2d(&tmO, smP + c * 16384, colQ + c * 64, row0);
+      for (int c = 0; c < FULLCH; ++c) tma_store_2d(&tmO, smP + c * 16384, colQ + c * 64, row0);
       tma_commit_group();
       tma_wait_group<0>();
     }
@@ -322,7 +334,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 // Softmax threads own one query row each (same mapping and Philox stream as forward).
 template <int HD>
 struct AttnBwdSmem {
-  static constexpr int CH = HD / 64;
+  static constexpr int CH = (HD + 63) / 64;
   static constexpr int TILE = 128 * 128 * CH;
   static constexpr int K_OFF = 0, V_OFF = TILE, Q_OFF = 2 * TILE, DO_OFF = 3 * TILE;
   static constexpr int P_OFF = 4 * TILE;            // 32 KB: P~ (bf16) / dQ staging (fp32) / dV staging
@@ -337,6 +349,7 @@ struct AttnBwdParams {
   const float* slopes;
   const float* lse;      // [B,H,T]
   const float* delta;    // [B,H,T] rowsum(dO o O)
+  bf16* dqkv;            // [B*T, 3*H*hd] (direct stores for a partial 64-column chunk)
   uint32_t drop_thr8;
   float inv_keep;
   const uint64_t* rng;
@@ -475,6 +488,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int etid = threadIdx.x - 64;
+    constexpr int SPLIT = (HD == 64) ? 32 : 64;
+    constexpr int FULLCH = HD / 64;
+    const int hc0 = hf ? SPLIT : 0, hcn = hf ? HD - SPLIT : SPLIT;
     const float slope2 = p.slopes ? p.slopes[h] * 1.4426950408889634f : 0.f;
     const bool use_drop = p.drop_thr8 != 0;
     const float keep_scale = use_drop ? p.inv_keep : 1.f;
@@ -575,11 +591,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_wait(dq_full, phs);
       tc_fence_after_sync();
       const int qrow0 = b * p.T + qb * ATT_BM;
-      constexpr int QC = HD / 2;  // dQ columns per thread
 #pragma unroll
-      for (int c32 = 0; c32 < QC / 32; ++c32) {
+      for (int c32 = 0; c32 < 2; ++c32) {
+        if (c32 * 32 >= hcn) break;
         uint32_t o[32];
-        tmem_ld_32x32b_x32(tS + lane_addr + hf * QC + c32 * 32, o);
+        tmem_ld_32x32b_x32(tS + lane_addr + hc0 + c32 * 32, o);
         tmem_wait_ld();
         uint8_t* orow = stage + c32 * 16384 + r * 128;
 #pragma unroll
@@ -594,8 +610,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-          for (int c32 = 0; c32 < QC / 32; ++c32)
-            tma_reduce_add_2d(&tmDQacc, (hh == 0 ? smP : smDS) + c32 * 16384, colQ + hh * QC + c32 * 32, qrow0);
+          for (int c32 = 0; c32 < 2; ++c32)
+            if (c32 * 32 < (hh ? HD - SPLIT : SPLIT))
+              tma_reduce_add_2d(&tmDQacc, (hh == 0 ? smP : smDS) + c32 * 16384, colQ + (hh ? SPLIT : 0) + c32 * 32, qrow0);
         tma_commit_group();
         tma_wait_group_read<0>();
       }
@@ -604,25 +621,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     // ---- epilogue: dV, dK (TMEM) -> bf16 -> smem -> TMA store into the V / K slots of dqkv
     mbar_wait(dq_full, (niter - 1) & 1);  // last commit covers every MMA
     tc_fence_after_sync();
-    constexpr int OC = HD / 2;
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       const uint32_t tsrc = which == 0 ? tDV : tDK;
       uint8_t* stg = which == 0 ? smP : smDS;
+      const int gcol0 = which == 0 ? colV : colK;
 #pragma unroll
-      for (int c = 0; c < OC / 32; ++c) {
+      for (int c = 0; c < 2; ++c) {
+        if (c * 32 >= hcn) break;
         uint32_t o[32];
-        const int col = hf * OC + c * 32;
+        const int col = hc0 + c * 32;
         tmem_ld_32x32b_x32(tsrc + lane_addr + col, o);
         tmem_wait_ld();
-        uint8_t* orow = stg + (col >> 6) * 16384 + r * 128;
+        uint4 o4[4];
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 o4 = make_uint4(pack_bf16(__uint_as_float(o[q4 * 8 + 0]), __uint_as_float(o[q4 * 8 + 1])),
-                                pack_bf16(__uint_as_float(o[q4 * 8 + 2]), __uint_as_float(o[q4 * 8 + 3])),
-                                pack_bf16(__uint_as_float(o[q4 * 8 + 4]), __uint_as_float(o[q4 * 8 + 5])),
-                                pack_bf16(__uint_as_float(o[q4 * 8 + 6]), __uint_as_float(o[q4 * 8 + 7])));
-          *reinterpret_cast<uint4*>(orow + (((((col & 63) >> 3) + q4) ^ (r & 7)) << 4)) = o4;
+        for (int q4 = 0; q4 < 4; ++q4)
+          o4[q4] = make_uint4(pack_bf16(__uint_as_float(o[q4 * 8 + 0]), __uint_as_float(o[q4 * 8 + 1])),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 2]), __uint_as_float(o[q4 * 8 + 3])),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 4]), __uint_as_float(o[q4 * 8 + 5])),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 6]), __uint_as_float(o[q4 * 8 + 7])));
+        if ((col >> 6) < FULLCH) {
+          uint8_t* orow = stg + (col >> 6) * 16384 + r * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(orow + (((((col & 63) >> 3) + q4) ^ (r & 7)) << 4)) = o4[q4];
+        } else {
+          bf16* gp = p.dqkv + (size_t)(krow + r) * (3 * D) + gcol0 + col;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) st_v4(gp + q4 * 8, o4[q4]);
         }
       }
       fence_proxy_async_smem();
@@ -630,7 +655,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if (etid == 0) {
         const int col = which == 0 ? colV : colK;
 #pragma unroll
-        for (int c = 0; c < CH; ++c) tma_store_2d(&tmDQKV, stg + c * 16384, col + c * 64, krow);
+        for (int c = 0; c < FULLCH; ++c) tma_store_2d(&tmDQKV, stg + c * 16384, col + c * 64, krow);
         tma_commit_group();
       }
     }
@@ -697,8 +722,8 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& to, const AttnPa
 // qkv: [B*T, 3*H*hd] bf16 (q | k | v, heads contiguous inside each); out: [B*T, H*hd]; lse: [B, H, T]
 int ztb_attn_fwd(const void* qkv, void* out, float* lse, const float* slopes, int B, int T, int H, int hd, float scale,
                  float dropout_p, const uint64_t* rng, uint32_t op_id, cudaStream_t st) {
-  if (T % 128 != 0 || (hd != 64 && hd != 128)) {
-    ztb_set_error("ztb_attn_fwd", "needs T % 128 == 0 and head_dim in {64, 128}", __FILE__, __LINE__);
+  if (T % 128 != 0 || (hd != 64 && hd != 96 && hd != 128)) {
+    ztb_set_error("ztb_attn_fwd", "needs T % 128 == 0 and head_dim in {64, 96, 128}", __FILE__, __LINE__);
     return -1;
   }
   const long long D = (long long)H * hd;
@@ -717,7 +742,8 @@ int ztb_attn_fwd(const void* qkv, void* out, float* lse, const float* slopes, in
   p.inv_keep = 256.f / (256.f - (float)p.drop_thr8);
   p.rng = rng; p.op_id = op_id;
   if (p.drop_thr8 && !rng) { ztb_set_error("ztb_attn_fwd", "dropout needs rng", __FILE__, __LINE__); return -1; }
-  return hd == 128 ? launch_fwd<128>(tq, to, p, st) : launch_fwd<64>(tq, to, p, st);
+  p.out = (bf16*)out;
+  return hd == 128 ? launch_fwd<128>(tq, to, p, st) : hd == 96 ? launch_fwd<96>(tq, to, p, st) : launch_fwd<64>(tq, to, p, st);
 }
 
 
@@ -741,8 +767,8 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const CUten
 int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dq_acc, float* delta,
                  const float* slopes, int B, int T, int H, int hd, float scale, float dropout_p, const uint64_t* rng,
                  uint32_t op_id, int sms, cudaStream_t st) {
-  if (T % 128 != 0 || (hd != 64 && hd != 128)) {
-    ztb_set_error("ztb_attn_bwd", "needs T % 128 == 0 and head_dim in {64, 128}", __FILE__, __LINE__);
+  if (T % 128 != 0 || (hd != 64 && hd != 96 && hd != 128)) {
+    ztb_set_error("ztb_attn_bwd", "needs T % 128 == 0 and head_dim in {64, 96, 128}", __FILE__, __LINE__);
     return -1;
   }
   const long long D = (long long)H * hd, rows = (long long)B * T;
@@ -766,7 +792,8 @@ int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float
   p.drop_thr8 = dropout_p > 0.f ? (thr ? thr : 1) : 0;
   p.inv_keep = 256.f / (256.f - (float)p.drop_thr8);
   p.rng = rng; p.op_id = op_id;
-  rc = hd == 128 ? launch_bwd<128>(tq, tdo, tdqkv, tacc, p, st) : launch_bwd<64>(tq, tdo, tdqkv, tacc, p, st);
+  p.dqkv = (bf16*)dqkv;
+  rc = hd == 128 ? launch_bwd<128>(tq, tdo, tdqkv, tacc, p, st) : hd == 96 ? launch_bwd<96>(tq, tdo, tdqkv, tacc, p, st) : launch_bwd<64>(tq, tdo, tdqkv, tacc, p, st);
   if (rc) return rc;
   size_t n = (size_t)rows * (D / 8);
   size_t g = (n + 255) / 256;

@@ -214,7 +214,7 @@ def _attn_ref(qkv, slopes, H, scale):
     return (p @ v).transpose(1, 2).reshape(B, T, H * hd), torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("B,T,H,hd", [(2, 128, 2, 128), (1, 256, 4, 64), (2, 512, 3, 128), (1, 1024, 2, 128)])
+@pytest.mark.parametrize("B,T,H,hd", [(2, 128, 2, 128), (1, 256, 4, 64), (2, 512, 3, 128), (1, 1024, 2, 128), (2, 256, 3, 96), (1, 512, 16, 96)])
 @pytest.mark.parametrize("alibi", [True, False])
 def test_attention_fwd(K, B, T, H, hd, alibi):
     from zero_transformer_b200.ops.reference import get_slopes
@@ -240,7 +240,7 @@ def test_attention_fwd_dropout_statistics(K):
     assert out.float().std().item() > 1e-3
 
 
-@pytest.mark.parametrize("B,T,H,hd", [(1, 128, 1, 128), (2, 256, 2, 128), (1, 512, 2, 64), (1, 1024, 2, 128)])
+@pytest.mark.parametrize("B,T,H,hd", [(1, 128, 1, 128), (2, 256, 2, 128), (1, 512, 2, 64), (1, 1024, 2, 128), (2, 256, 3, 96), (1, 512, 16, 96)])
 @pytest.mark.parametrize("alibi", [True, False])
 def test_attention_bwd(K, B, T, H, hd, alibi):
     from zero_transformer_b200.ops.attention_cuda import alibi_attention

@@ -9,7 +9,7 @@ from . import cuda as K
 def supported(qkv: torch.Tensor, n_head: int) -> bool:
     B, T, D3 = qkv.shape
     hd = D3 // 3 // n_head
-    return qkv.dtype == torch.bfloat16 and T % 128 == 0 and hd in (64, 128)
+    return qkv.dtype == torch.bfloat16 and T % 128 == 0 and hd in (64, 96, 128)
 
 
 class _Attention(torch.autograd.Function):

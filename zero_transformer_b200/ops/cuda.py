@@ -457,7 +457,7 @@ def attention(qkv, slopes, n_head, scale, p, training):
         if supported(qkv, n_head):
             return alibi_attention(qkv, slopes, n_head, scale, p if training else 0.0)
         if impl == "tc":
-            raise RuntimeError("tcgen05 attention needs bf16, T % 128 == 0 and head_dim in {64, 128}")
+            raise RuntimeError("tcgen05 attention needs bf16, T % 128 == 0 and head_dim in {64, 96, 128}")
     if impl in ("auto", "flash"):
         from flash_attn import flash_attn_qkvpacked_func
 
