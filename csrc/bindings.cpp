@@ -38,15 +38,17 @@ std::vector<at::Tensor> layernorm_fwd(const at::Tensor& x, const at::Tensor& w, 
 }
 
 std::vector<at::Tensor> layernorm_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& w, const at::Tensor& mean,
-                                      const at::Tensor& rstd) {
+                                      const at::Tensor& rstd, const c10::optional<at::Tensor>& dres) {
   need(is_bf16_cuda(dy) && is_bf16_cuda(x) && dy.is_contiguous() && x.is_contiguous(), "layernorm_bwd: bf16 contiguous");
   c10::cuda::CUDAGuard g(x.device());
   int D = x.size(-1);
   int M = x.numel() / D;
   auto dx = at::empty_like(x);
   auto dw = at::empty({D}, x.options().dtype(at::kFloat));
+  const void* dr = nullptr;
+  if (dres.has_value()) { need(is_bf16_cuda(*dres) && dres->is_contiguous() && dres->numel() == x.numel(), "layernorm_bwd: bad dres"); dr = dres->data_ptr(); }
   check(ztb_layernorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(), dx.data_ptr(),
-                          dw.data_ptr<float>(), M, D, num_sms(), stream()), "layernorm_bwd");
+                          dw.data_ptr<float>(), M, D, num_sms(), stream(), dr), "layernorm_bwd");
   return {dx, dw};
 }
 
@@ -281,7 +283,7 @@ void p2p_copy(int64_t dst_ptr, int64_t src_ptr, int64_t bytes) {
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("layernorm_fwd", &layernorm_fwd);
-  m.def("layernorm_bwd", &layernorm_bwd);
+  m.def("layernorm_bwd", &layernorm_bwd, py::arg("dy"), py::arg("x"), py::arg("w"), py::arg("mean"), py::arg("rstd"), py::arg("dres") = py::none());
   m.def("dropout_add", &dropout_add);
   m.def("embedding_fwd", &embedding_fwd);
   m.def("embedding_bwd_", &embedding_bwd_);

@@ -58,7 +58,7 @@ template <int NV>
 __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                             const bf16* __restrict__ w, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, bf16* __restrict__ dx,
-                                                            float* __restrict__ dw, int M) {
+                                                            float* __restrict__ dw, int M, const bf16* __restrict__ dres) {
   constexpr int D = NV * 256;
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float acc[NV * 8];
@@ -95,13 +95,15 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       uint4 uw = ld_v4(wr + i * 32 + lane);
+      uint4 ur = make_uint4(0, 0, 0, 0);  // gradient arriving through the residual branch (fused add)
+      if (dres != nullptr) ur = ld_nc_v4(reinterpret_cast<const uint4*>(dres + (size_t)row * D) + i * 32 + lane);
       uint32_t xs[4] = {px[i].x, px[i].y, px[i].z, px[i].w}, gs[4] = {pg[i].x, pg[i].y, pg[i].z, pg[i].w};
-      uint32_t ws[4] = {uw.x, uw.y, uw.z, uw.w}, os[4];
+      uint32_t ws[4] = {uw.x, uw.y, uw.z, uw.w}, rr[4] = {ur.x, ur.y, ur.z, ur.w}, os[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float2 xf = unpack_bf16(xs[k]), gf = unpack_bf16(gs[k]), wf = unpack_bf16(ws[k]);
+        float2 xf = unpack_bf16(xs[k]), gf = unpack_bf16(gs[k]), wf = unpack_bf16(ws[k]), rf = unpack_bf16(rr[k]);
         float xh0 = (xf.x - mu) * rs, xh1 = (xf.y - mu) * rs;
-        os[k] = pack_bf16(rs * (gf.x * wf.x - s1 - xh0 * s2), rs * (gf.y * wf.y - s1 - xh1 * s2));
+        os[k] = pack_bf16(rs * (gf.x * wf.x - s1 - xh0 * s2) + rf.x, rs * (gf.y * wf.y - s1 - xh1 * s2) + rf.y);
       }
       st_v4(dr + i * 32 + lane, make_uint4(os[0], os[1], os[2], os[3]));
     }
@@ -135,7 +137,7 @@ __global__ void layernorm_fwd_generic(const bf16* __restrict__ x, const bf16* __
 }
 __global__ void layernorm_bwd_generic(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
                                       const float* __restrict__ mean, const float* __restrict__ rstd,
-                                      bf16* __restrict__ dx, float* __restrict__ dw, int M, int D) {
+                                      bf16* __restrict__ dx, float* __restrict__ dw, int M, int D, const bf16* __restrict__ dres) {
   __shared__ float sh[2][4];
   int row = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float mu = mean[row], rs = rstd[row], s1 = 0.f, s2 = 0.f;
@@ -154,7 +156,8 @@ __global__ void layernorm_bwd_generic(const bf16* __restrict__ dy, const bf16* _
   for (int c = threadIdx.x; c < D; c += 128) {
     float xh = (__bfloat162float(x[(size_t)row * D + c]) - mu) * rs;
     float gw = __bfloat162float(dy[(size_t)row * D + c]) * __bfloat162float(w[c]);
-    dx[(size_t)row * D + c] = __float2bfloat16(rs * (gw - s1 - xh * s2));
+    float extra = dres ? __bfloat162float(dres[(size_t)row * D + c]) : 0.f;
+    dx[(size_t)row * D + c] = __float2bfloat16(rs * (gw - s1 - xh * s2) + extra);
   }
 }
 
@@ -359,13 +362,13 @@ int ztb_layernorm_fwd(const void* x, const void* w, void* y, float* mean, float*
 }
 
 int ztb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
-                      float* dw, int M, int D, int sms, cudaStream_t st) {
+                      float* dw, int M, int D, int sms, cudaStream_t st, const void* dres) {
   ZTB_CUDA_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * D, st));
   if (ln_fast(D)) {
     int nv = D / 256, grid = grid_for((M + 3) / 4, 1, sms * 4);
-    LN_DISPATCH(nv, layernorm_bwd_kernel, grid, (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M)
+    LN_DISPATCH(nv, layernorm_bwd_kernel, grid, (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, (const bf16*)dres)
   } else {
-    layernorm_bwd_generic<<<M, 128, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, D);
+    layernorm_bwd_generic<<<M, 128, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, D, (const bf16*)dres);
   }
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -193,11 +193,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (AG && warp == 7) {
+  } else if (AG && warp >= 6) {
     // ===================================================== all-gather warp (NVLink peer pulls)
     if constexpr (AG) {
       unsigned seen = 1u << ag.rank;
-      for (long long t = blockIdx.x; t < ag.total_tiles; t += gridDim.x) {
+      // two gather warps per CTA (warp 6 is free once it has allocated TMEM)
+      for (long long t = blockIdx.x * 2 + (warp - 6); t < ag.total_tiles; t += gridDim.x * 2) {
         int lo = 0, hi = ag.nseg - 1;
         while (lo < hi) {
           int mid = (lo + hi + 1) >> 1;

@@ -11,7 +11,7 @@ const char* ztb_last_error();
 // ---- elementwise.cu
 int ztb_layernorm_fwd(const void* x, const void* w, void* y, float* mean, float* rstd, int M, int D, float eps, cudaStream_t st);
 int ztb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
-                      float* dw, int M, int D, int sms, cudaStream_t st);
+                      float* dw, int M, int D, int sms, cudaStream_t st, const void* dres = nullptr);
 int ztb_dropout_add(const void* y, const void* res, void* out, size_t n, float p, const uint64_t* rng, uint32_t op_id,
                     int sms, cudaStream_t st);
 int ztb_embedding_fwd(const int* idx, const void* wte, void* out, int M, int D, int V, cudaStream_t st);

@@ -66,6 +66,10 @@ class LayerNorm(nn.Module):
     def forward(self, x):
         return ops.layernorm(x, self.weight, self.eps)
 
+    def forward_res(self, x):
+        """-> (normalised x, x for the residual branch)"""
+        return ops.layernorm_res(x, self.weight, self.eps)
+
 
 class Linear(nn.Module):
     """Bias-free ``(out, in)`` weight holder; the matmul happens in ``ops``."""
@@ -139,8 +143,10 @@ class TransformerBlock(nn.Module):
         self.mlp = MLPBlock(cfg)
 
     def forward(self, x, train: bool = False, layer_past=None, use_cache: bool = False):
-        x, present = self.attn(self.ln1(x), x, train, layer_past, use_cache)
-        x = self.mlp(self.ln2(x), x, train)
+        h, xr = self.ln1.forward_res(x)
+        x, present = self.attn(h, xr, train, layer_past, use_cache)
+        h, xr = self.ln2.forward_res(x)
+        x = self.mlp(h, xr, train)
         return x, present
 
 

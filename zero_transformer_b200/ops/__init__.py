@@ -40,6 +40,14 @@ def layernorm(x, weight, eps):
     return reference.layernorm(x, weight, eps)
 
 
+def layernorm_res(x, weight, eps):
+    """``(layernorm(x), x)``: the second output is ``x`` itself, to be used for the residual add, so
+    that on CUDA the residual gradient is folded into the LayerNorm backward kernel."""
+    if _use_cuda(x):
+        return _k().layernorm_res(x, weight, eps)
+    return reference.layernorm(x, weight, eps), x
+
+
 def linear(x, w):
     if _use_cuda(x):
         return _k().linear(x, w)

@@ -208,6 +208,36 @@ def layernorm(x, weight, eps):
     return _LayerNorm.apply(x, weight, eps)
 
 
+class _LayerNormRes(torch.autograd.Function):
+    """LayerNorm that also hands back its input for the residual connection.  Because both uses
+    of ``x`` leave through this node, backward receives the residual-branch gradient together with
+    the LayerNorm gradient and adds them inside the LayerNorm-backward kernel (no separate add)."""
+
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        xc = x.contiguous()
+        y, mean, rstd = _C.layernorm_fwd(xc, w.contiguous(), eps)
+        ctx.save_for_backward(xc, w, mean, rstd)
+        return y, xc.view_as(xc)
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        x, w, mean, rstd = ctx.saved_tensors
+        dr = dres.contiguous() if dres is not None else None
+        dx, dw = _C.layernorm_bwd(dy.contiguous(), x, w.contiguous(), mean, rstd, dr)
+        if CONFIG.fuse_wgrad and w.grad is not None:
+            if GRAD_MODE["accumulate"]:
+                w.grad.add_(dw)
+            else:
+                w.grad.copy_(dw)
+            return dx, None, None
+        return dx, dw.to(w.dtype), None
+
+
+def layernorm_res(x, weight, eps):
+    return _LayerNormRes.apply(x, weight, eps)
+
+
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w):
