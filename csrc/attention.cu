@@ -374,7 +374,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* kv_full = bars;        // TMA -> MMA (once)
   uint64_t* q_full = bars + 1;     // TMA -> MMA
   uint64_t* do_full = bars + 2;    // TMA -> MMA
-  uint64_t* qdo_empty = bars + 3;  // MMA commit -> TMA
+  uint64_t* q_empty = bars + 3;    // MMA commit (after dK) -> TMA
   uint64_t* s_full = bars + 4;     // MMA -> softmax
   uint64_t* dp_full = bars + 5;    // MMA -> softmax
   uint64_t* dp_empty = bars + 6;   // softmax(128) -> MMA
@@ -383,7 +383,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* pdv_done = bars + 9;   // MMA commit -> softmax (P smem free)
   uint64_t* dq_full = bars + 10;   // MMA commit -> softmax
   uint64_t* dq_drained = bars + 11;  // softmax(128) -> MMA (S/dQ columns free)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* do_empty = bars + 12;  // MMA commit (after dV) -> TMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jb = blockIdx.x;                   // key block (low j = most work, scheduled first)
@@ -396,7 +397,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmQKV); prefetch_tmap(&tmDO); prefetch_tmap(&tmDQKV); prefetch_tmap(&tmDQacc); }
   if (warp == 1 && lane == 0) {
-    mbar_init(kv_full, 1); mbar_init(q_full, 1); mbar_init(do_full, 1); mbar_init(qdo_empty, 1);
+    mbar_init(kv_full, 1); mbar_init(q_full, 1); mbar_init(do_full, 1); mbar_init(q_empty, 1); mbar_init(do_empty, 1);
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(dp_empty, 256); mbar_init(p_ready, 256);
     mbar_init(ds_ready, 256); mbar_init(pdv_done, 1); mbar_init(dq_full, 1); mbar_init(dq_drained, 256);
     fence_barrier_init();
@@ -418,13 +419,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
       for (int it = 0; it < niter; ++it) {
         const int qrow = b * p.T + (jb + it) * ATT_BM;
-        mbar_wait(qdo_empty, (it & 1) ^ 1);
-        mbar_expect_tx(q_full, L::TILE);
-#pragma unroll
-        for (int c = 0; c < CH; ++c) tma_load_2d(smQ + c * 16384, &tmQKV, q_full, colQ + c * 64, qrow);
+        mbar_wait(do_empty, (it & 1) ^ 1);   // dO is released first (after the dV MMA) ...
         mbar_expect_tx(do_full, L::TILE);
 #pragma unroll
         for (int c = 0; c < CH; ++c) tma_load_2d(smDO + c * 16384, &tmDO, do_full, colQ + c * 64, qrow);
+        mbar_wait(q_empty, (it & 1) ^ 1);    // ... Q after the dK MMA
+        mbar_expect_tx(q_full, L::TILE);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) tma_load_2d(smQ + c * 16384, &tmQKV, q_full, colQ + c * 64, qrow);
       }
     }
   } else if (warp == 1) {
@@ -465,6 +467,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           umma_f16_ss(tDV, make_smem_desc(p_addr + k * 2048, 16384, 1024, kSwizzle128B),
                       make_smem_desc(do_addr + k * 2048, 16384, 1024, kSwizzle128B), idesc_t, (it | k) != 0);
         umma_commit(pdv_done);
+        umma_commit(do_empty);
         // dK += dS^T Q ;  dQ = dS K
         mbar_wait(ds_ready, ph);
         tc_fence_after_sync();
@@ -472,12 +475,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         for (int k = 0; k < 8; ++k)
           umma_f16_ss(tDK, make_smem_desc(ds_addr + k * 2048, 16384, 1024, kSwizzle128B),
                       make_smem_desc(q_addr + k * 2048, 16384, 1024, kSwizzle128B), idesc_t, (it | k) != 0);
+        umma_commit(q_empty);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_f16_ss(tS, make_smem_desc(ds_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, kSwizzle128B),
                       make_smem_desc(k_addr + k * 2048, 16384, 1024, kSwizzle128B), idesc_q, k != 0);
         umma_commit(dq_full);
-        umma_commit(qdo_empty);
       }
     }
   } else {
@@ -537,7 +540,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           if (g & 1) keep[g >> 1] = (keep[g >> 1] & 0xffffu) | (bits << 16); else keep[g >> 1] = bits | 0xffff0000u;
         }
       }
-      // ---- P~ -> smem chunk hf
+      // ---- P~ -> smem chunk hf.  The buffers doubled as dQ staging in the previous iteration: make sure
+      // those bulk reduce-adds have finished reading smem (the wait is free by now -- it was issued
+      // a whole S/P phase ago).
+      if (it > 0) {
+        if (etid == 0) tma_wait_group_read<0>();
+        named_bar_sync(1, 256);
+      }
       {
         uint8_t* prow = smP + hf * 16384 + r * 128;
 #pragma unroll
@@ -614,13 +623,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             if (c32 * 32 < (hh ? HD - SPLIT : SPLIT))
               tma_reduce_add_2d(&tmDQacc, (hh == 0 ? smP : smDS) + c32 * 16384, colQ + (hh ? SPLIT : 0) + c32 * 32, qrow0);
         tma_commit_group();
-        tma_wait_group_read<0>();
       }
-      named_bar_sync(1, 256);  // staging buffers reusable as P / dS by the next iteration
     }
     // ---- epilogue: dV, dK (TMEM) -> bf16 -> smem -> TMA store into the V / K slots of dqkv
     mbar_wait(dq_full, (niter - 1) & 1);  // last commit covers every MMA
     tc_fence_after_sync();
+    if (etid == 0) tma_wait_group_read<0>();  // last dQ staging reads
+    named_bar_sync(1, 256);
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       const uint32_t tsrc = which == 0 ? tDV : tDK;
@@ -669,22 +678,44 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   }
 }
 
-// delta[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]   (one warp per (b,t,h) row)
+// delta[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d].  16-byte loads; hd/8 lanes cooperate on one (b,t,h) row.
+template <int HD>
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout,
-                                                         float* __restrict__ delta, int B, int T, int H, int hd) {
-  int row = blockIdx.x * 8 + (threadIdx.x >> 5);  // over B*T*H
-  if (row >= B * T * H) return;
-  int lane = threadIdx.x & 31;
-  int h = row % H, bt = row / H, t = bt % T, b = bt / T;
-  const bf162* po = reinterpret_cast<const bf162*>(o + (size_t)row * hd);
-  const bf162* pd = reinterpret_cast<const bf162*>(dout + (size_t)row * hd);
+                                                         float* __restrict__ delta, int B, int T, int H) {
+  constexpr int LPR = HD / 8;                       // lanes per row: 8, 12 or 16
+  constexpr int RPW = 32 / LPR;                     // rows per warp pass: 4, 2, 2
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, li = lane % LPR;
+  const long long nrows = (long long)B * T * H;
+  long long row = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + sub;
   float acc = 0.f;
-  for (int c = lane; c < hd / 2; c += 32) {
-    float2 a = __bfloat1622float2(po[c]), d = __bfloat1622float2(pd[c]);
-    acc += a.x * d.x + a.y * d.y;
+  const bool active = sub < RPW && row < nrows;
+  if (active) {
+    uint4 a = ld_nc_v4(o + row * HD + li * 8), d = ld_nc_v4(dout + row * HD + li * 8);
+    uint32_t as[4] = {a.x, a.y, a.z, a.w}, ds[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 x = unpack_bf16(as[k]), y = unpack_bf16(ds[k]);
+      acc += x.x * y.x + x.y * y.y;
+    }
   }
-  acc = warp_sum(acc);
-  if (lane == 0) delta[((size_t)b * H + h) * T + t] = acc;
+  // reduce over the LPR lanes of the row (LPR = 12 is not a power of two: go through 16-lane groups)
+  if constexpr (LPR == 12) {
+    // lanes [0,12) -> row 0, [12,24) -> row 1: shuffle-sum via explicit gathers
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) tot += __shfl_sync(0xffffffffu, acc, sub * 12 + k);
+    acc = tot;
+  } else {
+#pragma unroll
+    for (int off = LPR / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  }
+  if (active && li == 0) {
+    int h = (int)(row % H);
+    long long bt = row / H;
+    int t = (int)(bt % T), b = (int)(bt / T);
+    delta[((size_t)b * H + h) * T + t] = acc;
+  }
 }
 
 // dqkv[:, 0:D] = bf16(dq_acc)
@@ -772,7 +803,14 @@ int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float
     return -1;
   }
   const long long D = (long long)H * hd, rows = (long long)B * T;
-  attn_delta_kernel<<<(unsigned)((rows * H + 7) / 8), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, T, H, hd);
+  {
+    const long long nr = rows * H;
+    const int rpw = 32 / (hd / 8);
+    const unsigned blocks = (unsigned)((nr + 8 * rpw - 1) / (8 * rpw));
+    if (hd == 128) attn_delta_kernel<128><<<blocks, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, T, H);
+    else if (hd == 96) attn_delta_kernel<96><<<blocks, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, T, H);
+    else attn_delta_kernel<64><<<blocks, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, T, H);
+  }
   ZTB_CUDA_CHECK(cudaGetLastError());
   CUtensorMap tq, tdo, tdqkv, tacc;
   int rc = ztb_make_tmap_2d(&tq, qkv, 2, rows, 3 * D, 3 * D, 64, 128);
