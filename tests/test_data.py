@@ -75,3 +75,15 @@ def test_synthetic_is_deterministic_and_prefetcher_runs():
     pf = DevicePrefetcher(batch_iterator(SyntheticTokenDataset(100, 8, length=10), 4), "cpu")
     got = list(pf)
     assert len(got) == 2 and got[0].shape == (4, 8) and got[0].max() < 100
+
+
+def test_make_shards_roundtrip(tmp_path):
+    from zero_transformer_b200.data import make_shards
+
+    toks = np.arange(16 * 50, dtype=np.int32)
+    np.save(tmp_path / "toks.npy", toks)
+    idx = tmp_path / "index" / "train.index"
+    assert make_shards.main(["--tokens", str(tmp_path / "toks.npy"), "--out", str(tmp_path / "shards"), "--index", str(idx),
+                             "--max-context", "16", "--samples-per-shard", "20"]) == 0
+    rows = list(StreamingTokenDataset(str(idx), max_context=16, shuffle_buffer=1))
+    assert len(rows) == 50 and sorted(int(r[0]) for r in rows) == [16 * i for i in range(50)]

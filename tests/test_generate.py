@@ -48,3 +48,12 @@ def test_greedy_generation_is_deterministic_and_stops_on_eos():
     assert isinstance(generate_text(m, ByteTokenizer(), "ab", 4, seed=0), str)
     long = list(generate_from_prompt(m, list(range(40)), 5, sample=False))  # prompt longer than the window
     assert len(long) == 5
+
+
+def test_model_generate_matches_cached_greedy():
+    m = model_getter("test").eval()
+    ctx = [3, 1, 4, 1, 5]
+    full = m.generate(ctx, max_length=12)
+    assert full.shape == (1, 12) and full[0, :5].tolist() == ctx
+    cached = list(generate_from_prompt(m, ctx, 7, sample=False))
+    assert full[0, 5:].tolist() == cached

@@ -214,6 +214,20 @@ class Transformer(nn.Module):
             return logits, presents
         return logits
 
+    @torch.no_grad()
+    def generate(self, context, max_length: int, sample: bool = False) -> torch.Tensor:
+        """Greedy / sampled continuation without a KV cache -- the lm-eval-harness hook of the
+        reference ``GPT2.generate`` (``torch_compatability/GPT2.py:354-400``).  ``max_length`` counts
+        context + generated tokens; the context window is cropped to ``block_size``."""
+        dev = self.wte.weight.device
+        x = torch.as_tensor(context, dtype=torch.long, device=dev).view(1, -1)
+        for _ in range(max_length - x.shape[1]):
+            x_cond = x[:, -self.cfg.block_size:]
+            probs = torch.softmax(self.forward(x_cond, train=False)[:, -1, :].float(), dim=-1)
+            nxt = torch.multinomial(probs, 1) if sample else probs.argmax(-1, keepdim=True)
+            x = torch.cat([x, nxt], dim=1)
+        return x
+
     def decay_mask(self) -> dict:
         """``True`` for parameters that receive weight decay: everything with
         ndim >= 2 (reference mask ``main_zero.py:155-158``)."""
