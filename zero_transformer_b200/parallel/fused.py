@@ -107,7 +107,9 @@ class FusedComm:
             segs = [(r.offset + rank * r.chunk, r.shard_offset, r.chunk, int(r.decay)) for r in b.regions]
             t, tiles = pack_segments(segs, device, ADAM_TILE)
             self.adam.append((t, len(segs), tiles))
-            pl = [(r.offset + p * r.chunk, 0, r.chunk, p) for p in range(world) if p != rank for r in b.regions]
+            # rotated source order: at any moment every rank reads from a different owner, so no
+            # owner's NVLink egress is shared by several readers
+            pl = [(r.offset + p * r.chunk, 0, r.chunk, p) for p in self._peer_order(rank, world) for r in b.regions]
             t, tiles = pack_segments(pl, device, COPY_TILE)
             self.pull.append((t, len(pl), tiles))
         self.grad_ptrs = self._grad.ptrs[rank:] + self._grad.ptrs[:rank]  # local copy first
@@ -122,6 +124,10 @@ class FusedComm:
         self._pending = [False] * self.nb
         if world > 1:
             dist.barrier(group)
+
+    @staticmethod
+    def _peer_order(rank: int, world: int):
+        return [(rank + k) % world for k in range(1, world)]
 
     # flag addressing ----------------------------------------------------
     def _slot(self, kind: int, bucket: int, src: int) -> int:
@@ -183,9 +189,10 @@ class FusedComm:
             rest = [r for r in regs if r.name != first_region]
             assert len(lead) == 1
             r0 = lead[0]
-            pl = [(r0.offset + p * r0.chunk, 0, r0.chunk, p) for p in range(self.world) if p != self.rank]
+            order = self._peer_order(self.rank, self.world)
+            pl = [(r0.offset + p * r0.chunk, 0, r0.chunk, p) for p in order]
             n_b = len(pl)
-            pl += [(r.offset + p * r.chunk, 0, r.chunk, p) for p in range(self.world) if p != self.rank for r in rest]
+            pl += [(r.offset + p * r.chunk, 0, r.chunk, p) for p in order for r in rest]
             segs, tiles = pack_segments(pl, self.device, COPY_TILE)
             k = r0.shape[1]
             ok = r0.padded == r0.numel and (r0.chunk % k == 0)
