@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) dropout_add_kernel(const bf16* __restrict
   uint32_t thr = dropout_threshold(p);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
     uint4 uy = ld_nc_v4(reinterpret_cast<const uint4*>(y) + i);
-    uint4 r0 = ph(2 * i, stream), r1 = ph(2 * i + 1, stream);
+    uint4 r0 = ph.rounds<6>(2 * i, stream), r1 = ph.rounds<6>(2 * i + 1, stream);
     uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
     uint32_t ys[4] = {uy.x, uy.y, uy.z, uy.w};
     uint32_t rs[4] = {0, 0, 0, 0};

@@ -113,3 +113,24 @@ def test_overlapped_engine_backward_matches_plain_path():
         outs.append((eng.master.clone(), eng.flat_param.clone()))
     rel = (outs[0][0] - outs[1][0]).norm() / outs[0][0].norm()
     assert rel < 5e-3, rel.item()  # embedding-gradient atomics are order-nondeterministic; Adam amplifies near-zero grads
+
+
+def test_train_cli_on_gpu_with_eval_checkpoint_resume(tmp_path):
+    """The full driver on one GPU: fused engine, overlapped updates, eval cadence, checkpoint, resume."""
+    import json
+
+    from zero_transformer_b200 import train
+
+    args = ["--synthetic", "model.size=125m", "training.batch_size=4", "training.train_context=512", "data.max_context=1024",
+            "training.gradient_accumulation_steps=2", "training.evaluation_frequency=2", "training.maximum_evaluation_steps=1",
+            "training.warmup_steps=2", "training.total_steps=4", f"data.bucket_path={tmp_path}"]
+    assert train.main([*args, "--max-steps", "3"]) == 0
+    ck = tmp_path / "checkpoints"
+    assert (ck / "params" / "params_2.pt").exists()
+    recs = [json.loads(l) for l in open(ck / "metrics.jsonl") if '"step"' in l]
+    assert [r["step"] for r in recs] == [1, 2, 3] and "validation/loss" in recs[1]
+    assert all(r["train/loss"] == r["train/loss"] for r in recs)  # no NaN
+    assert all(9.0 < r["train/loss"] < 12.5 for r in recs)       # ~ln(50304) = 10.8 on random tokens
+    assert train.main(["--resume", *args]) == 0
+    recs = [json.loads(l) for l in open(ck / "metrics.jsonl") if '"step"' in l]
+    assert [r["step"] for r in recs][-2:] == [3, 4]
