@@ -17,6 +17,7 @@
 // 1/(1-p') factor is folded into the final 1/l normalisation.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "launchers.h"
@@ -189,6 +190,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     constexpr int FULLCH = HD / 64;               // 64-column chunks that leave through {64 x 128} TMA boxes
     const int hc0 = hf ? SPLIT : 0, hcn = hf ? HD - SPLIT : SPLIT;
     const float slope2 = p.slopes ? p.slopes[h] * 1.4426950408889634f : 0.f;
+    const float kk = slope2 / p.scale_log2;     // ALiBi slope in raw-score units
     const bool use_drop = p.drop_thr8 != 0;
     uint64_t seed = 0, stream = 0;
     if (use_drop) { seed = p.rng[0]; stream = p.rng[1] * 65536ull + p.op_id; }
@@ -209,27 +211,41 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
       tc_fence_before_sync();
       mbar_arrive(&s_empty[st]);
+      // Scores in log2 units: v_c = scale2 * u_c + base with u_c = S_c + kk * c (kk = slope / scale), so the
+      // first pass is one FMA (immediate column index) + max per element and the second pass one FMA +
+      // ex2 + add; the causal mask is only evaluated on the diagonal block.  4-way partial max / sum
+      // break the serial dependency chains.
       const int kv0 = j * ATT_BN + hf * 64;
       const float base = slope2 * (float)(kv0 - qi);
       const int cmax = r - hf * 64;          // columns > cmax are in the future (diagonal block only)
-      const bool diag = (j == qb);
-      float mx = -INFINITY;
+      float um[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (j == qb) {
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float v = fmaf(s[c], p.scale_log2, fmaf(slope2, (float)c, base));
-        if (diag && c > cmax) v = -INFINITY;
-        s[c] = v;
-        mx = fmaxf(mx, v);
+        for (int c = 0; c < 64; ++c) {
+          float u = fmaf(kk, (float)c, s[c]);
+          u = c > cmax ? -INFINITY : u;
+          s[c] = u;
+          um[c & 3] = fmaxf(um[c & 3], u);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          float u = fmaf(kk, (float)c, s[c]);
+          s[c] = u;
+          um[c & 3] = fmaxf(um[c & 3], u);
+        }
       }
+      float mx = fmaf(fmaxf(fmaxf(um[0], um[1]), fmaxf(um[2], um[3])), p.scale_log2, base);
       xch[(j & 1) * 256 + hf * 128 + r] = mx;
       named_bar_sync(3, 256);
       mx = fmaxf(mx, xch[(j & 1) * 256 + (hf ^ 1) * 128 + r]);
       float alpha = 1.f;
       if (mx > m + 8.f) { alpha = ex2_ftz(m - mx); m = mx; }  // lazy rescale; first block: alpha = 0
-      float sum = 0.f;
+      const float off = base - m;
+      float sm[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < 64; ++c) { s[c] = ex2_ftz(s[c] - m); sum += s[c]; }
-      l = l * alpha + sum;
+      for (int c = 0; c < 64; ++c) { s[c] = ex2_ftz(fmaf(s[c], p.scale_log2, off)); sm[c & 3] += s[c]; }
+      l = l * alpha + ((sm[0] + sm[1]) + (sm[2] + sm[3]));
       uint32_t pk[32];
       if (use_drop) {
 #pragma unroll
@@ -322,6 +338,500 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   }
 }
 
+
+// =====================================================================================
+// Forward, two-CTAs-per-SM variant (head_dim 128).  Profiling the 1-CTA/SM kernel showed ~40 % of
+// its time in exposed per-CTA prologue/epilogue latency (TMEM alloc, Q load, O store) and role
+// hand-offs: a second co-resident CTA fills those bubbles.  To fit two CTAs (<= 113 KB smem, 256 TMEM
+// columns, <= 170 registers) the KV block shrinks to 64 keys and each of the 4 softmax warps owns
+// full 64-column rows again (no cross-warp row-max exchange).
+constexpr int ATT3_THREADS = 192;
+constexpr int ATT3_BN = 64;
+struct Attn3Smem {
+  static constexpr int Q_OFF = 0;                  // [128 x 128] bf16 = 32 KB (also O staging)
+  static constexpr int K_OFF = 32768;              // 2 stages x [64 x 128] = 2 x 16 KB
+  static constexpr int V_OFF = 65536;              // 2 stages x 16 KB
+  static constexpr int P_OFF = 98304;              // [128 x 64] bf16 = 16 KB
+  static constexpr int BAR_OFF = 114688;
+  static constexpr int TOTAL = 115712;             // 113 KB (multiple of 1 KB): two CTAs + 2 x 1 KB reserved = 228 KB
+};
+
+__global__ void __launch_bounds__(ATT3_THREADS, 2)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                 const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
+  constexpr int HD = 128;
+  using L = Attn3Smem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need a 1 KB-aligned base
+  uint8_t* smQ = smem + L::Q_OFF;
+  uint8_t* smK = smem + L::K_OFF;
+  uint8_t* smV = smem + L::V_OFF;
+  uint8_t* smP = smem + L::P_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;      // 2
+  uint64_t* v_full = bars + 3;      // 2
+  uint64_t* kv_empty = bars + 5;    // 2
+  uint64_t* s_full = bars + 7;      // 2
+  uint64_t* s_empty = bars + 9;     // 2 (count 128)
+  uint64_t* p_ready = bars + 11;    // count 128
+  uint64_t* pv_done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = gridDim.x - 1 - blockIdx.x;
+  const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  const int D = p.H * HD;
+  const int nblk = 2 * qb + 2;                       // 64-key blocks 0 .. 2qb+1
+  const int row0 = b * p.T + qb * ATT_BM;
+  const int colQ = h * HD, colK = D + h * HD, colV = 2 * D + h * HD;
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmKV); prefetch_tmap(&tmO); }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1);
+                                  mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); }
+    mbar_init(p_ready, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;          // 2 x 64 columns
+  const uint32_t tO = tmem_base + 128;    // 128 columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 32768);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) tma_load_2d(smQ + c * 16384, &tmQ, q_full, colQ + c * 64, row0);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        const int krow = b * p.T + j * ATT3_BN;
+        mbar_expect_tx(&k_full[st], 16384);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tma_load_2d(smK + st * 16384 + c * 8192, &tmKV, &k_full[st], colK + c * 64, krow);
+        mbar_expect_tx(&v_full[st], 16384);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tma_load_2d(smV + st * 16384 + c * 8192, &tmKV, &v_full[st], colV + c * 64, krow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT3_BN, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, HD, 0, 1);
+      const uint32_t q_addr = smem_u32(smQ), p_addr = smem_u32(smP);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&k_full[st], (j >> 1) & 1);
+        mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t k_addr = smem_u32(smK + st * 16384);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_f16_ss(tS + st * 64, make_smem_desc(q_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, kSwizzle128B),
+                      make_smem_desc(k_addr + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024, kSwizzle128B), idesc_s, k != 0);
+        umma_commit(&s_full[st]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        if (j + 1 < nblk) issue_s(j + 1);
+        mbar_wait(p_ready, j & 1);
+        mbar_wait(&v_full[st], (j >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t v_addr = smem_u32(smV + st * 16384);
+#pragma unroll
+        for (int k = 0; k < ATT3_BN / 16; ++k)
+          umma_f16_ss(tO, make_smem_desc(p_addr + k * 32, 16, 1024, kSwizzle128B),
+                      make_smem_desc(v_addr + k * 2048, 8192, 1024, kSwizzle128B), idesc_o, (j | k) != 0);
+        umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int qi = qb * ATT_BM + r;
+    const float slope2 = p.slopes ? p.slopes[h] * 1.4426950408889634f : 0.f;
+    const float kk = slope2 / p.scale_log2;
+    const bool use_drop = p.drop_thr8 != 0;
+    uint64_t seed = 0, stream = 0;
+    if (use_drop) { seed = p.rng[0]; stream = p.rng[1] * 65536ull + p.op_id; }
+    Philox ph(seed);
+    const uint64_t row_id = (uint64_t)bh * p.T + qi;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      const int st = j & 1;
+      mbar_wait(&s_full[st], (j >> 1) & 1);
+      tc_fence_after_sync();
+      float s[64];
+      {
+        uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+        tmem_ld_32x32b_x32(tS + lane_addr + st * 64, sr);
+        tmem_ld_32x32b_x32(tS + lane_addr + st * 64 + 32, sr + 32);
+        tmem_wait_ld();
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&s_empty[st]);
+      const int kv0 = j * ATT3_BN;
+      const float base = slope2 * (float)(kv0 - qi);
+      const int cmax = qi - kv0;                     // columns > cmax are in the future
+      float um[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (j >= 2 * qb) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          float u = fmaf(kk, (float)c, s[c]);
+          u = c > cmax ? -INFINITY : u;
+          s[c] = u;
+          um[c & 3] = fmaxf(um[c & 3], u);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          float u = fmaf(kk, (float)c, s[c]);
+          s[c] = u;
+          um[c & 3] = fmaxf(um[c & 3], u);
+        }
+      }
+      const float mx = fmaf(fmaxf(fmaxf(um[0], um[1]), fmaxf(um[2], um[3])), p.scale_log2, base);
+      float alpha = 1.f;
+      if (mx > m + 8.f) { alpha = ex2_ftz(m - mx); m = mx; }   // m stays finite: block 0 always has column 0 visible
+      const float off = base - m;
+      float sm[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 64; ++c) { s[c] = ex2_ftz(fmaf(s[c], p.scale_log2, off)); sm[c & 3] += s[c]; }
+      l = l * alpha + ((sm[0] + sm[1]) + (sm[2] + sm[3]));
+      uint32_t pk[32];
+      if (use_drop) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 rb = attn_dropout_bits(ph, row_id, (uint32_t)(j * 4 + g), stream);
+          uint32_t w[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            uint32_t b0 = (w[e >> 2] >> ((e & 3) * 8)) & 0xFF, b1 = (w[(e + 1) >> 2] >> (((e + 1) & 3) * 8)) & 0xFF;
+            pk[g * 8 + (e >> 1)] = pack_bf16(b0 >= p.drop_thr8 ? s[g * 16 + e] : 0.f, b1 >= p.drop_thr8 ? s[g * 16 + e + 1] : 0.f);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) pk[c] = pack_bf16(s[2 * c], s[2 * c + 1]);
+      }
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after_sync();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tO + lane_addr + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+            tmem_st_32x32b_x32(tO + lane_addr + c * 32, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      uint8_t* prow = smP + r * 128;
+#pragma unroll
+      for (int c16 = 0; c16 < 8; ++c16)
+        *reinterpret_cast<uint4*>(prow + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[c16 * 4], pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]);
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(p_ready);
+    }
+    // ---- epilogue: O / l -> bf16 -> staging (Q region: every S MMA has retired) -> TMA store; LSE
+    mbar_wait(pv_done, (nblk - 1) & 1);
+    tc_fence_after_sync();
+    const float inv = (use_drop ? p.inv_keep : 1.f) / l;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tO + lane_addr + c * 32, o);
+      tmem_wait_ld();
+      uint8_t* orow = smQ + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint4 o4 = make_uint4(pack_bf16(__uint_as_float(o[q4 * 8 + 0]) * inv, __uint_as_float(o[q4 * 8 + 1]) * inv),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 2]) * inv, __uint_as_float(o[q4 * 8 + 3]) * inv),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 4]) * inv, __uint_as_float(o[q4 * 8 + 5]) * inv),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 6]) * inv, __uint_as_float(o[q4 * 8 + 7]) * inv));
+        *reinterpret_cast<uint4*>(orow + ((((c & 1) * 4 + q4) ^ (r & 7)) << 4)) = o4;
+      }
+    }
+    p.lse[(size_t)bh * p.T + qi] = (m + log2f(l)) * 0.6931471805599453f;
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (threadIdx.x == 64) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) tma_store_2d(&tmO, smQ + c * 16384, colQ + c * 64, row0);
+      tma_commit_group();
+      tma_wait_group<0>();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+// =====================================================================================
+// Forward, ping-pong variant (head_dim 128, T % 256 == 0): one CTA owns TWO adjacent 128-query tiles
+// of a (batch, head).  Both tiles consume the same K_j / V_j (single-buffered, separately released:
+// K after the two S MMAs, V after the two PV MMAs, so the next K/V loads overlap the softmax), and
+// each tile has its own softmax warpgroup (one query row per thread).  While warpgroup A runs the
+// softmax of its tile the tensor core works on tile B and vice versa -- the FA3/FA4 ping-pong --
+// instead of idling through the S -> softmax -> P -> PV dependency chain of a single tile.
+//   warps 0-3  softmax tile A      warps 4-7  softmax tile B      warp 8 TMA      warp 9 MMA
+// TMEM: S_A, S_B (2 x 128 columns) + O_A, O_B (2 x 128 columns) = 512 columns.
+constexpr int ATT2_THREADS = 384;
+
+struct Attn2Smem {
+  static constexpr int TILE = 32768;                 // [128 x 128] bf16
+  static constexpr int Q_OFF = 0;                    // 2 tiles
+  static constexpr int K_OFF = 2 * TILE, V_OFF = 3 * TILE;
+  static constexpr int P_OFF = 4 * TILE;             // 2 tiles (also O staging)
+  static constexpr int BAR_OFF = 6 * TILE;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
+  constexpr int HD = 128;
+  using L = Attn2Smem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smQ = smem + L::Q_OFF;
+  uint8_t* smK = smem + L::K_OFF;
+  uint8_t* smV = smem + L::V_OFF;
+  uint8_t* smP = smem + L::P_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* q_full = bars;           // 1
+  uint64_t* k_full = bars + 1;       // 1
+  uint64_t* k_empty = bars + 2;      // 1
+  uint64_t* v_full = bars + 3;       // 1
+  uint64_t* v_empty = bars + 4;      // 1
+  uint64_t* s_full = bars + 5;       // 2 (per tile)
+  uint64_t* s_empty = bars + 7;      // 2, count 128
+  uint64_t* p_ready = bars + 9;      // 2, count 128
+  uint64_t* pv_done = bars + 11;     // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pr = gridDim.x - 1 - blockIdx.x;          // pair index, heavy first
+  const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  const int D = p.H * HD;
+  const int qb0 = 2 * pr;                              // tile A = q block qb0, tile B = qb0 + 1
+  const int nblk = qb0 + 2;                            // KV blocks 0 .. qb0+1 (tile A stops at qb0)
+  const int row0 = b * p.T + qb0 * ATT_BM;
+  const int colQ = h * HD, colK = D + h * HD, colV = 2 * D + h * HD;
+
+  if (warp == 8 && lane == 0) { prefetch_tmap(&tmQKV); prefetch_tmap(&tmO); }
+  if (warp == 9 && lane == 0) {
+    mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); mbar_init(&p_ready[i], 128); mbar_init(&pv_done[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 8 && lane == 0) {
+      // ===================================================== TMA producer
+      mbar_expect_tx(q_full, 2 * L::TILE);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tma_load_2d(smQ + t * L::TILE + c * 16384, &tmQKV, q_full, colQ + c * 64, row0 + t * ATT_BM);
+      for (int j = 0; j < nblk; ++j) {
+        const int krow = b * p.T + j * ATT_BN;
+        mbar_wait(k_empty, (j & 1) ^ 1);
+        mbar_expect_tx(k_full, L::TILE);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tma_load_2d(smK + c * 16384, &tmQKV, k_full, colK + c * 64, krow);
+        mbar_wait(v_empty, (j & 1) ^ 1);
+        mbar_expect_tx(v_full, L::TILE);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tma_load_2d(smV + c * 16384, &tmQKV, v_full, colV + c * 64, krow);
+      }
+    } else if (warp == 9 && lane == 0) {
+      // ===================================================== MMA issuer
+      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, HD, 0, 1);
+      const uint32_t k_addr = smem_u32(smK), v_addr = smem_u32(smV);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nblk; ++j) {
+        const int nt = (j <= qb0) ? 2 : 1;             // tile A has no work in the last block
+        const int t0 = (j <= qb0) ? 0 : 1;
+        mbar_wait(k_full, j & 1);
+        for (int t = t0; t < 2; ++t) {
+          const int jt = j;                            // tile-local block counter == j (tiles start at 0)
+          mbar_wait(&s_empty[t], (jt & 1) ^ 1);
+          tc_fence_after_sync();
+          const uint32_t q_addr = smem_u32(smQ + t * L::TILE);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) {
+            const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+            umma_f16_ss(tmem_base + t * 128, make_smem_desc(q_addr + off, 16, 1024, kSwizzle128B),
+                        make_smem_desc(k_addr + off, 16, 1024, kSwizzle128B), idesc_s, k != 0);
+          }
+          umma_commit(&s_full[t]);
+        }
+        umma_commit(k_empty);
+        mbar_wait(v_full, j & 1);
+        for (int t = t0; t < 2; ++t) {
+          mbar_wait(&p_ready[t], j & 1);
+          tc_fence_after_sync();
+          const uint32_t p_addr = smem_u32(smP + t * L::TILE);
+#pragma unroll
+          for (int k = 0; k < ATT_BN / 16; ++k) {
+            uint64_t da = make_smem_desc(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, kSwizzle128B);
+            uint64_t db = make_smem_desc(v_addr + k * 2048, 16384, 1024, kSwizzle128B);
+            umma_f16_ss(tmem_base + 256 + t * 128, da, db, idesc_o, (j | k) != 0);
+          }
+          umma_commit(&pv_done[t]);
+        }
+        umma_commit(v_empty);
+        (void)nt;
+      }
+    }
+  } else {
+    // ===================================================== softmax warpgroups (tile t = warp / 4)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int t = warp >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int qb = qb0 + t;
+    const int qi = qb * ATT_BM + r;
+    const int myblk = qb + 1;                          // this tile's KV blocks 0..qb
+    const uint32_t tS = tmem_base + t * 128, tO = tmem_base + 256 + t * 128;
+    uint8_t* myP = smP + t * L::TILE;
+    const float slope2 = p.slopes ? p.slopes[h] * 1.4426950408889634f : 0.f;
+    const bool use_drop = p.drop_thr8 != 0;
+    uint64_t seed = 0, stream = 0;
+    if (use_drop) { seed = p.rng[0]; stream = p.rng[1] * 65536ull + p.op_id; }
+    Philox ph(seed);
+    const uint64_t row_id = (uint64_t)bh * p.T + qi;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < myblk; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after_sync();
+      float s[128];
+      {
+        uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tS + lane_addr + c * 32, sr + c * 32);
+        tmem_wait_ld();
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&s_empty[t]);
+      const float base = slope2 * (float)(j * ATT_BN - qi);
+      const bool diag = (j == qb);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; ++c) {
+        float v = fmaf(s[c], p.scale_log2, fmaf(slope2, (float)c, base));
+        if (diag && c > r) v = -INFINITY;
+        s[c] = v;
+        mx = fmaxf(mx, v);
+      }
+      float alpha = 1.f;
+      if (mx > m + 8.f) { alpha = ex2_ftz(m - mx); m = mx; }
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 128; ++c) { s[c] = ex2_ftz(s[c] - m); sum += s[c]; }
+      l = l * alpha + sum;
+      if (j > 0) {
+        mbar_wait(&pv_done[t], (j - 1) & 1);           // P smem free, O stable
+        tc_fence_after_sync();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tO + lane_addr + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+            tmem_st_32x32b_x32(tO + lane_addr + c * 32, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      uint8_t* prow = myP + r * 128;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {                    // 16 keys per group -> two 16-byte stores
+        uint32_t pk[8];
+        if (use_drop) {
+          uint4 rb = attn_dropout_bits(ph, row_id, (uint32_t)(j * 8 + g), stream);
+          uint32_t w[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            uint32_t b0 = (w[e >> 2] >> ((e & 3) * 8)) & 0xFF, b1 = (w[(e + 1) >> 2] >> (((e + 1) & 3) * 8)) & 0xFF;
+            pk[e >> 1] = pack_bf16(b0 >= p.drop_thr8 ? s[g * 16 + e] : 0.f, b1 >= p.drop_thr8 ? s[g * 16 + e + 1] : 0.f);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pk[e] = pack_bf16(s[g * 16 + 2 * e], s[g * 16 + 2 * e + 1]);
+        }
+        const int c16 = g * 2;
+        *reinterpret_cast<uint4*>(prow + (c16 >> 3) * 16384 + (((c16 & 7) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(prow + ((c16 + 1) >> 3) * 16384 + ((((c16 + 1) & 7) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&p_ready[t]);
+    }
+    // ---- epilogue of this tile
+    mbar_wait(&pv_done[t], (myblk - 1) & 1);
+    tc_fence_after_sync();
+    const float inv = (use_drop ? p.inv_keep : 1.f) / l;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tO + lane_addr + c * 32, o);
+      tmem_wait_ld();
+      uint8_t* orow = myP + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint4 o4 = make_uint4(pack_bf16(__uint_as_float(o[q4 * 8 + 0]) * inv, __uint_as_float(o[q4 * 8 + 1]) * inv),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 2]) * inv, __uint_as_float(o[q4 * 8 + 3]) * inv),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 4]) * inv, __uint_as_float(o[q4 * 8 + 5]) * inv),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 6]) * inv, __uint_as_float(o[q4 * 8 + 7]) * inv));
+        *reinterpret_cast<uint4*>(orow + ((((c & 1) * 4 + q4) ^ (r & 7)) << 4)) = o4;
+      }
+    }
+    p.lse[(size_t)bh * p.T + qi] = (m + log2f(l)) * 0.6931471805599453f;
+    fence_proxy_async_smem();
+    named_bar_sync(1 + t, 128);
+    if (quarter == 0 && lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) tma_store_2d(&tmO, myP + c * 16384, colQ + c * 64, row0 + t * ATT_BM);
+      tma_commit_group();
+      tma_wait_group<0>();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
 
 // =====================================================================================
 // Backward.  One CTA per (batch, head, 128-key block j); K_j and V_j stay resident in smem and the
@@ -495,6 +1005,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     constexpr int FULLCH = HD / 64;
     const int hc0 = hf ? SPLIT : 0, hcn = hf ? HD - SPLIT : SPLIT;
     const float slope2 = p.slopes ? p.slopes[h] * 1.4426950408889634f : 0.f;
+    const float kk = slope2 / p.scale_log2;
     const bool use_drop = p.drop_thr8 != 0;
     const float keep_scale = use_drop ? p.inv_keep : 1.f;
     uint64_t seed = 0, stream = 0;
@@ -510,6 +1021,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const size_t ridx = (size_t)bh * p.T + qi;
       const float lse2 = p.lse[ridx] * 1.4426950408889634f;
       const float delta = p.delta[ridx];
+      const float kscale = keep_scale * p.scale, ndelta = -delta * p.scale;
       const uint64_t row_id = (uint64_t)bh * p.T + qi;
       // ---- P = exp2(S*c + alibi - lse)
       mbar_wait(s_full, phs);
@@ -522,11 +1034,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tmem_wait_ld();
       }
       const float base = slope2 * (float)(kv0 - qi) - lse2;
-      const bool diag = (it == 0);
+      if (it == 0) {  // diagonal block: causal mask
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float v = ex2_ftz(fmaf(s[c], p.scale_log2, fmaf(slope2, (float)c, base)));
-        s[c] = (diag && c > cmax) ? 0.f : v;
+        for (int c = 0; c < 64; ++c) {
+          float v = ex2_ftz(fmaf(fmaf(kk, (float)c, s[c]), p.scale_log2, base));
+          s[c] = c > cmax ? 0.f : v;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) s[c] = ex2_ftz(fmaf(fmaf(kk, (float)c, s[c]), p.scale_log2, base));
       }
       uint32_t keep[2] = {0xffffffffu, 0xffffffffu};  // bit c set = keep
       if (use_drop) {
@@ -583,9 +1099,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int cc = q4 * 8 + e * 2;
-              float d0 = ((kb >> cc) & 1u) ? __uint_as_float(dpv[cc]) * keep_scale : 0.f;
-              float d1 = ((kb >> (cc + 1)) & 1u) ? __uint_as_float(dpv[cc + 1]) * keep_scale : 0.f;
-              pk[e] = pack_bf16(s[c32 * 32 + cc] * (d0 - delta) * p.scale, s[c32 * 32 + cc + 1] * (d1 - delta) * p.scale);
+              // dS = P * (D o dP / keep - delta) * scale, with the constants folded: FMA + select + MUL
+              float d0 = ((kb >> cc) & 1u) ? fmaf(__uint_as_float(dpv[cc]), kscale, ndelta) : ndelta;
+              float d1 = ((kb >> (cc + 1)) & 1u) ? fmaf(__uint_as_float(dpv[cc + 1]), kscale, ndelta) : ndelta;
+              pk[e] = pack_bf16(s[c32 * 32 + cc] * d0, s[c32 * 32 + cc + 1] * d1);
             }
             const int c16 = c32 * 4 + q4;
             *reinterpret_cast<uint4*>(drow + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -736,6 +1253,24 @@ using namespace ztb;
 int ztb_make_tmap_2d(CUtensorMap* tm, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
                      int box_cols, int box_rows);
 
+static int ztb_attn_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ZTB_ATTN_FWD"); v = e ? atoi(e) : 3; }
+  return v;  // 1 = one CTA/SM (column-split softmax), 2 = two-tile ping-pong, 3 = two CTAs/SM (64-key blocks)
+}
+
+static int launch_fwd2(const CUtensorMap& tq, const CUtensorMap& to, const AttnParams& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    ZTB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
+    configured = true;
+  }
+  dim3 grid(p.T / 256, p.B * p.H);
+  attn_fwd2_kernel<<<grid, ATT2_THREADS, Attn2Smem::TOTAL, st>>>(tq, to, p);
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 template <int HD>
 static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& to, const AttnParams& p, cudaStream_t st) {
   auto kern = attn_fwd_kernel<HD>;
@@ -774,6 +1309,21 @@ int ztb_attn_fwd(const void* qkv, void* out, float* lse, const float* slopes, in
   p.rng = rng; p.op_id = op_id;
   if (p.drop_thr8 && !rng) { ztb_set_error("ztb_attn_fwd", "dropout needs rng", __FILE__, __LINE__); return -1; }
   p.out = (bf16*)out;
+  if (hd == 128 && ztb_attn_variant() == 3) {
+    CUtensorMap tkv;
+    rc = ztb_make_tmap_2d(&tkv, qkv, 2, (long long)B * T, 3 * D, 3 * D, 64, 64);
+    if (rc) return rc;
+    static bool configured = false;
+    if (!configured) {
+      ZTB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
+      configured = true;
+    }
+    dim3 grid(T / ATT_BM, B * H);
+    attn_fwd3_kernel<<<grid, ATT3_THREADS, Attn3Smem::TOTAL, st>>>(tq, tkv, to, p);
+    ZTB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
+  if (hd == 128 && T % 256 == 0 && ztb_attn_variant() == 2) return launch_fwd2(tq, to, p, st);
   return hd == 128 ? launch_fwd<128>(tq, to, p, st) : hd == 96 ? launch_fwd<96>(tq, to, p, st) : launch_fwd<64>(tq, to, p, st);
 }
 
