@@ -14,6 +14,8 @@
 // finishes its kernel, then ztb_signal (same stream) does __threadfence_system() +
 // st.release.sys into each peer's pad; consumers spin with ld.acquire.sys at kernel start.  Values
 // are monotonically increasing step numbers, so pads never need resetting.
+#include <stdio.h>
+
 #include "common.cuh"
 #include "launchers.h"
 
@@ -29,6 +31,15 @@ ZTB_DEVINL int ld_acquire_sys_i32(const int* p) {
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+ZTB_DEVINL unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Failure detection: a peer that died (or a protocol bug) must not hang the GPU until the job's
+// wall-clock limit.  Every cross-rank spin gives up after kFlagTimeoutNs and traps, which surfaces as a
+// CUDA error on the host ("unspecified launch failure") instead of a silent hang.
+constexpr unsigned long long kFlagTimeoutNs = 120ull * 1000000000ull;
 ZTB_DEVINL void st_release_sys_i32(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -38,7 +49,15 @@ ZTB_DEVINL void st_release_sys_i32(int* p, int v) {
 // this rank's own backward needs to make progress.
 __global__ void wait_flags_kernel(const int* flags, int n, int value) {
   if ((int)threadIdx.x < n) {
-    while (ld_acquire_sys_i32(flags + threadIdx.x) < value) __nanosleep(128);
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys_i32(flags + threadIdx.x) < value) {
+      __nanosleep(128);
+      if (globaltimer_ns() - t0 > kFlagTimeoutNs) {
+        printf("[ztb] rank flag wait timed out: slot %d holds %d, expected >= %d (peer %d stalled or dead)\n", (int)threadIdx.x,
+               ld_acquire_sys_i32(flags + threadIdx.x), value, (int)threadIdx.x);
+        __trap();
+      }
+    }
   }
 }
 

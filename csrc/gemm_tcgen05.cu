@@ -207,7 +207,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const ZtbSegment sg = ag.segs[lo];
         const int src = sg.decay;
         if (!((seen >> src) & 1u)) {   // the owner has published this step's chunk?
-          if (lane == 0) while (ld_acquire_sys_s32(ag.shard_ready + src) < ag.epoch) __nanosleep(64);
+          if (lane == 0) {
+            unsigned long long t0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (ld_acquire_sys_s32(ag.shard_ready + src) < ag.epoch) {
+              __nanosleep(64);
+              unsigned long long t1;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+              if (t1 - t0 > 120ull * 1000000000ull) __trap();  // owner never published its shard: fail loudly
+            }
+          }
           __syncwarp();
           seen |= 1u << src;
         }

@@ -61,9 +61,11 @@ class Zero1Engine:
         grad_dtype: Optional[torch.dtype] = None,
         decay_mask: Optional[Dict[str, bool]] = None,
         bucket_of=default_bucket_of,
+        ag_gemm: bool = True,
     ):
         self.model = model
         self.group = group
+        self.ag_gemm = bool(ag_gemm)
         self.rank, self.world = _dist_info(group)
         self.lr_fn = lr_fn
         self.weight_decay = float(weight_decay)
@@ -170,7 +172,7 @@ class Zero1Engine:
         ``ops.linear`` runs the all-gather-fused GEMM when that bucket still has to be gathered."""
         import os
 
-        if self.world == 1 or os.environ.get("ZTB_AG_GEMM", "1") != "1":
+        if self.world == 1 or not self.ag_gemm or os.environ.get("ZTB_AG_GEMM", "1") != "1":
             return
         fused = []
         for i, blk in enumerate(getattr(model, "blocks", [])):
