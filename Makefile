@@ -9,3 +9,5 @@ bench:
 	python bench.py --gpus 1 --steps 8 --warmup 3
 style:
 	python -m compileall -q zero_transformer_b200 tests bench.py
+sanitize:
+	bash bench/sanitize.sh
