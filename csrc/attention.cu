@@ -860,6 +860,7 @@ struct AttnBwdParams {
   const float* lse;      // [B,H,T]
   const float* delta;    // [B,H,T] rowsum(dO o O)
   bf16* dqkv;            // [B*T, 3*H*hd] (direct stores for a partial 64-column chunk)
+  unsigned long long* dbg;  // optional: per-phase cycle counters of softmax thread 0 (bench/attn_timing.py)
   uint32_t drop_thr8;
   float inv_keep;
   const uint64_t* rng;
@@ -1024,7 +1025,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const float kscale = keep_scale * p.scale, ndelta = -delta * p.scale;
       const uint64_t row_id = (uint64_t)bh * p.T + qi;
       // ---- P = exp2(S*c + alibi - lse)
+      long long tk0 = clock64();
       mbar_wait(s_full, phs);
+      long long tk1 = clock64();
       tc_fence_after_sync();
       float s[64];
       {
@@ -1044,16 +1047,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
         for (int c = 0; c < 64; ++c) s[c] = ex2_ftz(fmaf(fmaf(kk, (float)c, s[c]), p.scale_log2, base));
       }
-      uint32_t keep[2] = {0xffffffffu, 0xffffffffu};  // bit c set = keep
+      // Dropout decision folded into the sign of P: s[c] = +P (kept) or -P (dropped).  The packed P~ for the
+      // dV MMA is then max(s, 0) (the 1/keep factor moves to the dV epilogue) and the dS pass reads the
+      // decision back from the sign -- 3 instructions per element (byte-permute, compare, signed select)
+      // instead of building and re-testing bit masks.
       if (use_drop) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 rb = attn_dropout_bits(ph, row_id, (uint32_t)(jb * 8 + hf * 4 + g), stream);
           uint32_t w[4] = {rb.x, rb.y, rb.z, rb.w};
-          uint32_t bits = 0;
 #pragma unroll
-          for (int e = 0; e < 16; ++e) bits |= (((w[e >> 2] >> ((e & 3) * 8)) & 0xFF) >= p.drop_thr8 ? 1u : 0u) << e;
-          if (g & 1) keep[g >> 1] = (keep[g >> 1] & 0xffffu) | (bits << 16); else keep[g >> 1] = bits | 0xffff0000u;
+          for (int e = 0; e < 16; ++e) {
+            const uint32_t byte = __byte_perm(w[e >> 2], 0u, 0x4440u | (uint32_t)(e & 3));
+            const float v = s[g * 16 + e];
+            s[g * 16 + e] = byte >= p.drop_thr8 ? v : -v;
+          }
         }
       }
       // ---- P~ -> smem chunk hf.  The buffers doubled as dQ staging in the previous iteration: make sure
@@ -1071,9 +1079,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = c16 * 8 + e * 2;
-            float a0 = ((keep[c >> 5] >> (c & 31)) & 1u) ? s[c] * keep_scale : 0.f;
-            float a1 = ((keep[(c + 1) >> 5] >> ((c + 1) & 31)) & 1u) ? s[c + 1] * keep_scale : 0.f;
-            pk[e] = pack_bf16(a0, a1);
+            pk[e] = pack_bf16(fmaxf(s[c], 0.f), fmaxf(s[c + 1], 0.f));
           }
           *reinterpret_cast<uint4*>(prow + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
@@ -1082,7 +1088,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_fence_before_sync();
       mbar_arrive(p_ready);
       // ---- dS = P o (D o dP / keep - delta) * scale  -> smem chunk hf
+      long long tk2 = clock64();
       mbar_wait(dp_full, phs);
+      long long tk3 = clock64();
       tc_fence_after_sync();
       {
         uint8_t* drow = smDS + hf * 16384 + r * 128;
@@ -1092,17 +1100,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           tmem_ld_32x32b_x32(tDP + lane_addr + hf * 64 + c32 * 32, dpv);
           tmem_wait_ld();
           if (c32 == 1) { tc_fence_before_sync(); mbar_arrive(dp_empty); }
-          const uint32_t kb = keep[c32];
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int cc = q4 * 8 + e * 2;
-              // dS = P * (D o dP / keep - delta) * scale, with the constants folded: FMA + select + MUL
-              float d0 = ((kb >> cc) & 1u) ? fmaf(__uint_as_float(dpv[cc]), kscale, ndelta) : ndelta;
-              float d1 = ((kb >> (cc + 1)) & 1u) ? fmaf(__uint_as_float(dpv[cc + 1]), kscale, ndelta) : ndelta;
-              pk[e] = pack_bf16(s[c32 * 32 + cc] * d0, s[c32 * 32 + cc + 1] * d1);
+              // dS = P * (D o dP / keep - delta) * scale, constants folded; D is the sign of s (see above)
+              const float s0 = s[c32 * 32 + cc], s1 = s[c32 * 32 + cc + 1];
+              float d0 = s0 > 0.f ? fmaf(__uint_as_float(dpv[cc]), kscale, ndelta) : ndelta;
+              float d1 = s1 > 0.f ? fmaf(__uint_as_float(dpv[cc + 1]), kscale, ndelta) : ndelta;
+              pk[e] = pack_bf16(fabsf(s0) * d0, fabsf(s1) * d1);
             }
             const int c16 = c32 * 4 + q4;
             *reinterpret_cast<uint4*>(drow + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -1113,8 +1121,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_arrive(ds_ready);
       // ---- drain dQ: each half moves HD/2 fp32 columns TMEM -> its staging buffer -> TMA reduce-add.
       // P buffer is free once the dV MMA retired, dS buffer once dK/dQ retired (dq_full).
+      long long tk4 = clock64();
       mbar_wait(pdv_done, phs);
       mbar_wait(dq_full, phs);
+      long long tk5 = clock64();
       tc_fence_after_sync();
       const int qrow0 = b * p.T + qb * ATT_BM;
 #pragma unroll
@@ -1141,6 +1151,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
               tma_reduce_add_2d(&tmDQacc, (hh == 0 ? smP : smDS) + c32 * 16384, colQ + (hh ? SPLIT : 0) + c32 * 32, qrow0);
         tma_commit_group();
       }
+      if (p.dbg != nullptr && etid == 0) {
+        long long tk6 = clock64();
+        atomicAdd(p.dbg + 0, (unsigned long long)(tk1 - tk0));   // wait S
+        atomicAdd(p.dbg + 1, (unsigned long long)(tk2 - tk1));   // P phase (ld S, exp, dropout, st.shared)
+        atomicAdd(p.dbg + 2, (unsigned long long)(tk3 - tk2));   // wait dP
+        atomicAdd(p.dbg + 3, (unsigned long long)(tk4 - tk3));   // dS phase
+        atomicAdd(p.dbg + 4, (unsigned long long)(tk5 - tk4));   // wait dV done + dQ ready
+        atomicAdd(p.dbg + 5, (unsigned long long)(tk6 - tk5));   // dQ drain
+        atomicAdd(p.dbg + 6, 1ull);
+      }
     }
     // ---- epilogue: dV, dK (TMEM) -> bf16 -> smem -> TMA store into the V / K slots of dqkv
     mbar_wait(dq_full, (niter - 1) & 1);  // last commit covers every MMA
@@ -1152,6 +1172,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const uint32_t tsrc = which == 0 ? tDV : tDK;
       uint8_t* stg = which == 0 ? smP : smDS;
       const int gcol0 = which == 0 ? colV : colK;
+      const float osc = which == 0 ? keep_scale : 1.f;   // dV = (D o P)^T dO / keep: the 1/keep factor is applied here
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         if (c * 32 >= hcn) break;
@@ -1162,10 +1183,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         uint4 o4[4];
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
-          o4[q4] = make_uint4(pack_bf16(__uint_as_float(o[q4 * 8 + 0]), __uint_as_float(o[q4 * 8 + 1])),
-                              pack_bf16(__uint_as_float(o[q4 * 8 + 2]), __uint_as_float(o[q4 * 8 + 3])),
-                              pack_bf16(__uint_as_float(o[q4 * 8 + 4]), __uint_as_float(o[q4 * 8 + 5])),
-                              pack_bf16(__uint_as_float(o[q4 * 8 + 6]), __uint_as_float(o[q4 * 8 + 7])));
+          o4[q4] = make_uint4(pack_bf16(__uint_as_float(o[q4 * 8 + 0]) * osc, __uint_as_float(o[q4 * 8 + 1]) * osc),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 2]) * osc, __uint_as_float(o[q4 * 8 + 3]) * osc),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 4]) * osc, __uint_as_float(o[q4 * 8 + 5]) * osc),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 6]) * osc, __uint_as_float(o[q4 * 8 + 7]) * osc));
         if ((col >> 6) < FULLCH) {
           uint8_t* orow = stg + (col >> 6) * 16384 + r * 128;
 #pragma unroll
@@ -1347,7 +1368,7 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const CUten
 // delta: [B,H,T] fp32 scratch.
 int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dq_acc, float* delta,
                  const float* slopes, int B, int T, int H, int hd, float scale, float dropout_p, const uint64_t* rng,
-                 uint32_t op_id, int sms, cudaStream_t st) {
+                 uint32_t op_id, int sms, cudaStream_t st, unsigned long long* dbg) {
   if (T % 128 != 0 || (hd != 64 && hd != 96 && hd != 128)) {
     ztb_set_error("ztb_attn_bwd", "needs T % 128 == 0 and head_dim in {64, 96, 128}", __FILE__, __LINE__);
     return -1;
@@ -1381,6 +1402,7 @@ int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float
   p.inv_keep = 256.f / (256.f - (float)p.drop_thr8);
   p.rng = rng; p.op_id = op_id;
   p.dqkv = (bf16*)dqkv;
+  p.dbg = dbg;
   rc = hd == 128 ? launch_bwd<128>(tq, tdo, tdqkv, tacc, p, st) : hd == 96 ? launch_bwd<96>(tq, tdo, tdqkv, tacc, p, st) : launch_bwd<64>(tq, tdo, tdqkv, tacc, p, st);
   if (rc) return rc;
   size_t n = (size_t)rows * (D / 8);

@@ -80,4 +80,4 @@ int ztb_attn_fwd(const void* qkv, void* out, float* lse, const float* slopes, in
                  float dropout_p, const uint64_t* rng, uint32_t op_id, cudaStream_t st);
 int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dq_acc, float* delta,
                  const float* slopes, int B, int T, int H, int hd, float scale, float dropout_p, const uint64_t* rng,
-                 uint32_t op_id, int sms, cudaStream_t st);
+                 uint32_t op_id, int sms, cudaStream_t st, unsigned long long* dbg = nullptr);
