@@ -88,6 +88,8 @@ class ClockSampler:
 def main():
     args = parse()
     if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
         print(json.dumps({"impl": "reference", "unavailable": "reference is JAX/Flax on TPU only (main_zero.py:200-201 raises on GPU); "
                           "no setup.py/pyproject (pip: not installable) and jax/flax/optax/omegaconf are absent offline"}))
         return 0
