@@ -101,3 +101,23 @@ def test_flax_msgpack_import(tmp_path):
     np.testing.assert_array_equal(ours["blocks.0.mlp.fc_in.weight"].numpy(), tree["params"]["TransformerBlock_0"]["MLPBlock_0"]["fc_in"]["kernel"].T)
     m = Transformer(GPTConfig(embedding_dim=D, vocab_size=V, num_head=2, block_size=8, N=2))
     m.load_state_dict(ours, strict=True)
+
+
+def test_torch_compat_model_getter_loads_reference_pth(tmp_path):
+    from zero_transformer_b200.models.torch_compat import model_getter
+    from zero_transformer_b200.parallel.partition import create_opt_spec, layout_for, set_partitions_zero
+
+    m = _tiny(gelu="erf")
+    out = tmp_path / "t.pth"
+    save_reference_pth(dict(m.named_parameters()), str(out), num_head=4, num_ctx=8)
+    cfgp = tmp_path / "model_config.yaml"
+    cfgp.write_text("test:\n  embedding_dim: 64\n  vocab_size: 256\n  num_head: 4\n  num_ctx: 8\n  N: 2\n")
+    m2 = model_getter("test", str(cfgp), str(out))
+    x = torch.randint(0, 256, (1, 8))
+    with torch.no_grad():
+        torch.testing.assert_close(m2(x), m(x))
+    spec = set_partitions_zero({n: tuple(p.shape) for n, p in m.named_parameters()}, 4)
+    assert spec["wte.weight"] == ("dp", None) and spec["ln_f.weight"] == ("dp",)
+    assert set(create_opt_spec(spec)) == {"master", "mu", "nu", "count"}
+    L = layout_for(m, 4)
+    assert L.total == L.shard_total * 4

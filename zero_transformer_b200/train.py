@@ -104,6 +104,7 @@ class Trainer:
                             "Total Devices": env.world})
             self.sink = MetricsSink(self.workdir, run_cfg, project=str(d.get("wandb_project", "") or ""), enabled=env.is_main)
         self._timer = StepTimer(env.device)
+        self._nvtx = on_gpu and os.environ.get("ZTB_NVTX", "0") == "1"   # NVTX ranges for nsys/ncu timelines
         self._graph = None
 
     # ------------------------------------------------------------------ data
@@ -131,6 +132,9 @@ class Trainer:
         """One optimizer update from a ``(rows_per_rank, max_context)`` token
         batch already on the device.  Returns device tensors (no host sync)."""
         self.model.train()
+        nvtx = self._nvtx
+        if nvtx:
+            torch.cuda.nvtx.range_push("train_step")
         mbs = to_micro_batches(rechunk(batch, self.train_context), self.accum)
         self.engine.zero_grad(lazy=True)
         loss_sum = None
@@ -138,7 +142,12 @@ class Trainer:
             loss = self.model.loss(mbs[i], train=True)
             self.engine.backward(loss, last=(i == self.accum - 1))
             loss_sum = loss.detach() if loss_sum is None else loss_sum + loss.detach()
+        if nvtx:
+            torch.cuda.nvtx.range_push("optimizer_step")
         lr = self.engine.step()
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
+            torch.cuda.nvtx.range_pop()
         mean_loss = loss_sum / self.accum
         return {"train/loss": mean_loss, "lr": lr}
 

@@ -88,6 +88,26 @@ def save_checkpoint(engine, workdir: str, step: int, keep: int = 5, sharded: boo
         dist.barrier()
 
 
+def save_checkpoint_params(engine, workdir: str, step: int, keep: int = 5) -> None:
+    """Reference name (``main_zero.py:58-71``): parameters only.  Collective."""
+    pdir = _dirs(workdir)[0]
+    params = engine.full_params_fp32(0)
+    if engine.rank == 0:
+        os.makedirs(pdir, exist_ok=True)
+        _atomic_save({"step": step, "params": params}, os.path.join(pdir, f"params_{step}.pt"))
+        _prune(pdir, "params_", keep)
+
+
+def save_checkpoint_optimizer(engine, workdir: str, step: int, keep: int = 5) -> None:
+    """Reference name (``main_zero.py:74-93``): gathered Adam moments only.  Collective."""
+    odir = _dirs(workdir)[1]
+    st = engine.consolidated_state(0)
+    if engine.rank == 0:
+        os.makedirs(odir, exist_ok=True)
+        _atomic_save({"step": step, "exp_avg": st["exp_avg"], "exp_avg_sq": st["exp_avg_sq"]}, os.path.join(odir, f"optimizer_{step}.pt"))
+        _prune(odir, "optimizer_", keep)
+
+
 def latest_step(workdir: str) -> Optional[int]:
     steps = _steps(_dirs(workdir)[0], "params_")
     return steps[-1] if steps else None
