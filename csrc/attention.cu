@@ -846,10 +846,10 @@ template <int HD>
 struct AttnBwdSmem {
   static constexpr int CH = (HD + 63) / 64;
   static constexpr int TILE = 128 * 128 * CH;
-  static constexpr int K_OFF = 0, V_OFF = TILE, Q_OFF = 2 * TILE, DO_OFF = 3 * TILE;
-  static constexpr int P_OFF = 4 * TILE;            // 32 KB: P~ (bf16) / dQ staging (fp32) / dV staging
-  static constexpr int DS_OFF = 4 * TILE + 32768;   // 32 KB: dS (bf16) / dK staging
-  static constexpr int BAR_OFF = 4 * TILE + 65536;
+  static constexpr int K_OFF = 0, V_OFF = TILE, Q_OFF = 2 * TILE /* 2 stages */, DO_OFF = 4 * TILE;
+  static constexpr int P_OFF = 5 * TILE;            // 32 KB: P~ (bf16) / dQ staging (fp32) / dV staging
+  static constexpr int DS_OFF = 5 * TILE + 32768;   // 32 KB: dS (bf16) / dK staging
+  static constexpr int BAR_OFF = 5 * TILE + 65536;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
 
@@ -883,18 +883,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint8_t* smDS = smem + L::DS_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* kv_full = bars;        // TMA -> MMA (once)
-  uint64_t* q_full = bars + 1;     // TMA -> MMA
+  uint64_t* q_full = bars + 1;     // TMA -> MMA, stage 0 (stage 1 = bars + 14)
   uint64_t* do_full = bars + 2;    // TMA -> MMA
-  uint64_t* q_empty = bars + 3;    // MMA commit (after dK) -> TMA
+  uint64_t* q_empty = bars + 3;    // MMA commit (after dK) -> TMA, stage 0 (stage 1 = bars + 15)
   uint64_t* s_full = bars + 4;     // MMA -> softmax
   uint64_t* dp_full = bars + 5;    // MMA -> softmax
-  uint64_t* dp_empty = bars + 6;   // softmax(128) -> MMA
+  uint64_t* s_empty = bars + 6;    // softmax(256) -> MMA: S columns read, S of the next iteration may be issued
   uint64_t* p_ready = bars + 7;    // softmax(128) -> MMA
   uint64_t* ds_ready = bars + 8;   // softmax(128) -> MMA
   uint64_t* pdv_done = bars + 9;   // MMA commit -> softmax (P smem free)
   uint64_t* dq_full = bars + 10;   // MMA commit -> softmax
-  uint64_t* dq_drained = bars + 11;  // softmax(128) -> MMA (S/dQ columns free)
+  uint64_t* dq_drained = bars + 11;  // softmax(256) -> MMA: dQ drained, the dP/dQ columns are free
   uint64_t* do_empty = bars + 12;  // MMA commit (after dV) -> TMA
+  uint64_t* q_full1 = bars + 14;
+  uint64_t* q_empty1 = bars + 15;
+  uint64_t* dk_done = bars + 16;   // MMA commit after the last dK: every MMA has completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -909,7 +912,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmQKV); prefetch_tmap(&tmDO); prefetch_tmap(&tmDQKV); prefetch_tmap(&tmDQacc); }
   if (warp == 1 && lane == 0) {
     mbar_init(kv_full, 1); mbar_init(q_full, 1); mbar_init(do_full, 1); mbar_init(q_empty, 1); mbar_init(do_empty, 1);
-    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(dp_empty, 256); mbar_init(p_ready, 256);
+    mbar_init(q_full1, 1); mbar_init(q_empty1, 1); mbar_init(dk_done, 1);
+    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(s_empty, 256); mbar_init(p_ready, 256);
     mbar_init(ds_ready, 256); mbar_init(pdv_done, 1); mbar_init(dq_full, 1); mbar_init(dq_drained, 256);
     fence_barrier_init();
   }
@@ -930,14 +934,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
       for (int it = 0; it < niter; ++it) {
         const int qrow = b * p.T + (jb + it) * ATT_BM;
-        mbar_wait(do_empty, (it & 1) ^ 1);   // dO is released first (after the dV MMA) ...
+        {                                     // Q is double-buffered: stage it&1 was released by dK of iteration it-2
+          uint64_t* qe = (it & 1) ? q_empty1 : q_empty;
+          uint64_t* qf = (it & 1) ? q_full1 : q_full;
+          mbar_wait(qe, ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(qf, L::TILE);
+#pragma unroll
+          for (int c = 0; c < CH; ++c) tma_load_2d(smQ + (it & 1) * L::TILE + c * 16384, &tmQKV, qf, colQ + c * 64, qrow);
+        }
+        mbar_wait(do_empty, (it & 1) ^ 1);   // dO (single stage) is released by the dV MMA of the previous iteration
         mbar_expect_tx(do_full, L::TILE);
 #pragma unroll
         for (int c = 0; c < CH; ++c) tma_load_2d(smDO + c * 16384, &tmDO, do_full, colQ + c * 64, qrow);
-        mbar_wait(q_empty, (it & 1) ^ 1);    // ... Q after the dK MMA
-        mbar_expect_tx(q_full, L::TILE);
-#pragma unroll
-        for (int c = 0; c < CH; ++c) tma_load_2d(smQ + c * 16384, &tmQKV, q_full, colQ + c * 64, qrow);
       }
     }
   } else if (warp == 1) {
@@ -948,21 +956,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const uint32_t k_addr = smem_u32(smK), v_addr = smem_u32(smV), q_addr = smem_u32(smQ), do_addr = smem_u32(smDO);
       const uint32_t p_addr = smem_u32(smP), ds_addr = smem_u32(smDS);
       mbar_wait(kv_full, 0);
-      for (int it = 0; it < niter; ++it) {
-        const uint32_t ph = it & 1;
-        // S = Q K^T
-        mbar_wait(q_full, ph);
-        mbar_wait(dq_drained, ph ^ 1);
+      // S_i = Q_i K^T is issued at the END of iteration i-1 (Q is double-buffered and dQ no longer shares
+      // the S columns), so it runs on the tensor core while the softmax warps drain dQ_{i-1}.
+      auto issue_s = [&](int it) {
+        mbar_wait((it & 1) ? q_full1 : q_full, (it >> 1) & 1);
+        if (it > 0) mbar_wait(s_empty, (it - 1) & 1);
         tc_fence_after_sync();
+        const uint32_t qa = q_addr + (it & 1) * L::TILE;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
           const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_f16_ss(tS, make_smem_desc(q_addr + off, 16, 1024, kSwizzle128B), make_smem_desc(k_addr + off, 16, 1024, kSwizzle128B), idesc_s, k != 0);
+          umma_f16_ss(tS, make_smem_desc(qa + off, 16, 1024, kSwizzle128B), make_smem_desc(k_addr + off, 16, 1024, kSwizzle128B), idesc_s, k != 0);
         }
         umma_commit(s_full);
-        // dP = dO V^T
+      };
+      issue_s(0);
+      for (int it = 0; it < niter; ++it) {
+        const uint32_t ph = it & 1;
+        const uint32_t qa = q_addr + (it & 1) * L::TILE;
+        // dP = dO V^T  (its TMEM columns also receive dQ: wait until the previous dQ has been drained)
         mbar_wait(do_full, ph);
-        mbar_wait(dp_empty, ph ^ 1);
+        if (it > 0) mbar_wait(dq_drained, (it - 1) & 1);
         tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
@@ -979,19 +993,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                       make_smem_desc(do_addr + k * 2048, 16384, 1024, kSwizzle128B), idesc_t, (it | k) != 0);
         umma_commit(pdv_done);
         umma_commit(do_empty);
-        // dK += dS^T Q ;  dQ = dS K
+        // dK += dS^T Q ;  dQ = dS K  (dQ lands in the dP columns: dP was consumed to build dS)
         mbar_wait(ds_ready, ph);
         tc_fence_after_sync();
+        // dQ first: the softmax warps are waiting for it; dK and the next S then run under the dQ drain
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_f16_ss(tDP, make_smem_desc(ds_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, kSwizzle128B),
+                      make_smem_desc(k_addr + k * 2048, 16384, 1024, kSwizzle128B), idesc_q, k != 0);
+        umma_commit(dq_full);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_f16_ss(tDK, make_smem_desc(ds_addr + k * 2048, 16384, 1024, kSwizzle128B),
-                      make_smem_desc(q_addr + k * 2048, 16384, 1024, kSwizzle128B), idesc_t, (it | k) != 0);
-        umma_commit(q_empty);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_f16_ss(tS, make_smem_desc(ds_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, kSwizzle128B),
-                      make_smem_desc(k_addr + k * 2048, 16384, 1024, kSwizzle128B), idesc_q, k != 0);
-        umma_commit(dq_full);
+                      make_smem_desc(qa + k * 2048, 16384, 1024, kSwizzle128B), idesc_t, (it | k) != 0);
+        umma_commit((it & 1) ? q_empty1 : q_empty);
+        umma_commit(dk_done);
+        if (it + 1 < niter) issue_s(it + 1);
       }
     }
   } else {
@@ -1036,6 +1053,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tmem_ld_32x32b_x32(tS + lane_addr + hf * 64 + 32, sr + 32);
         tmem_wait_ld();
       }
+      tc_fence_before_sync();
+      mbar_arrive(s_empty);
       const float base = slope2 * (float)(kv0 - qi) - lse2;
       if (it == 0) {  // diagonal block: causal mask
 #pragma unroll
@@ -1099,7 +1118,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           uint32_t dpv[32];
           tmem_ld_32x32b_x32(tDP + lane_addr + hf * 64 + c32 * 32, dpv);
           tmem_wait_ld();
-          if (c32 == 1) { tc_fence_before_sync(); mbar_arrive(dp_empty); }
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             uint32_t pk[4];
@@ -1120,7 +1138,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       mbar_arrive(ds_ready);
       // ---- drain dQ: each half moves HD/2 fp32 columns TMEM -> its staging buffer -> TMA reduce-add.
-      // P buffer is free once the dV MMA retired, dS buffer once dK/dQ retired (dq_full).
+      // P buffer is free once the dV MMA retired, dS buffer once dQ and dK retired (dq_full, dk_done).
       long long tk4 = clock64();
       mbar_wait(pdv_done, phs);
       mbar_wait(dq_full, phs);
@@ -1131,8 +1149,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       for (int c32 = 0; c32 < 2; ++c32) {
         if (c32 * 32 >= hcn) break;
         uint32_t o[32];
-        tmem_ld_32x32b_x32(tS + lane_addr + hc0 + c32 * 32, o);
+        tmem_ld_32x32b_x32(tDP + lane_addr + hc0 + c32 * 32, o);
         tmem_wait_ld();
+        if (hf && c32 == 0) mbar_wait(dk_done, phs);   // half 1 stages into the dS buffer, which the dK MMA is still reading
         uint8_t* orow = stage + c32 * 16384 + r * 128;
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4)
@@ -1163,7 +1182,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
     // ---- epilogue: dV, dK (TMEM) -> bf16 -> smem -> TMA store into the V / K slots of dqkv
-    mbar_wait(dq_full, (niter - 1) & 1);  // last commit covers every MMA
+    mbar_wait(dk_done, (niter - 1) & 1);  // last commit covers every MMA
     tc_fence_after_sync();
     if (etid == 0) tma_wait_group_read<0>();  // last dQ staging reads
     named_bar_sync(1, 256);
