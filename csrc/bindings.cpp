@@ -120,7 +120,7 @@ void ce_bwd_(at::Tensor& logits, const at::Tensor& labels, const at::Tensor& lse
 // C[M,N] (+)= op(A) * op(B)^T ; see launchers.h ZtbGemmArgs.  a_mn: A given as [K,M]; b_mn: B given as [K,N].
 at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tensor> C_, int64_t epilogue,
                 const c10::optional<at::Tensor>& aux_in, c10::optional<at::Tensor> aux_out, double p,
-                const c10::optional<at::Tensor>& rng, int64_t op_id, bool accumulate, bool a_mn, bool b_mn, bool two_cta) {
+                const c10::optional<at::Tensor>& rng, int64_t op_id, bool accumulate, bool a_mn, bool b_mn, bool two_cta, bool no_split) {
   need(is_bf16_cuda(A) && is_bf16_cuda(B) && A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "gemm: A, B must be 2-D bf16 CUDA with unit inner stride");
   c10::cuda::CUDAGuard g(A.device());
   ZtbGemmArgs a{};
@@ -141,7 +141,7 @@ at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tens
   a.lda = A.stride(0); a.ldb = B.stride(0); a.ldc = C.stride(0);
   a.epilogue = (int)epilogue;
   a.accumulate = accumulate; a.c_is_fp32 = C.scalar_type() == at::kFloat;
-  a.a_mn_major = a_mn; a.b_mn_major = b_mn; a.two_cta = two_cta;
+  a.a_mn_major = a_mn; a.b_mn_major = b_mn; a.two_cta = two_cta; a.no_split = no_split;
   a.p = (float)p; a.op_id = (uint32_t)op_id;
   if (aux_in.has_value()) {
     need(is_bf16_cuda(*aux_in) && aux_in->dim() == 2 && aux_in->size(0) == a.M && aux_in->size(1) == a.N && aux_in->stride(1) == 1, "gemm: bad aux_in");
@@ -294,7 +294,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ce_bwd_", &ce_bwd_);
   m.def("gemm", &gemm, py::arg("A"), py::arg("B"), py::arg("C") = py::none(), py::arg("epilogue") = 0, py::arg("aux_in") = py::none(),
         py::arg("aux_out") = py::none(), py::arg("p") = 0.0, py::arg("rng") = py::none(), py::arg("op_id") = 0,
-        py::arg("accumulate") = false, py::arg("a_mn") = false, py::arg("b_mn") = false, py::arg("two_cta") = false);
+        py::arg("accumulate") = false, py::arg("a_mn") = false, py::arg("b_mn") = false, py::arg("two_cta") = false, py::arg("no_split") = false);
   m.def("gemm_ag", &gemm_ag);
   m.def("adamw_shard", &adamw_shard);
   m.def("segment_struct_size", &segment_struct_size);

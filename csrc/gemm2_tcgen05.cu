@@ -37,7 +37,28 @@ struct GemmParams {
   const uint64_t* rng;
   uint32_t op_id;
   int tiles_m, tiles_n, num_tiles;
+  // Tail splitting: the first `full_tiles` tiles (a multiple of the pair count) are whole-K work units;
+  // each of the remaining `tail` tiles is cut into `split` K-ranges whose partial sums meet in C through
+  // bulk reduce-adds (C pre-initialised by the launcher).  split == 1: every tile is one unit.
+  int full_tiles, tail, split;
+  int* chain;   // split > 1: [tail][16] per-(tile, CTA, epilogue warp) count of K-ranges already reduced into C
 };
+
+struct Unit { int tile, kb0, kb1, partial, part; };
+// Units are dealt round-robin: unit u of a pair is pair + i * num_pairs.  Tail units are ordered K-range
+// major, so the pairs working concurrently on tiles that share an A/B panel read the same K range (L2 reuse).
+ZTB_DEVINL bool get_unit(int u, const GemmParams& p, int kblocks, Unit& w) {
+  if (u < p.full_tiles) { w.tile = u; w.kb0 = 0; w.kb1 = kblocks; w.partial = 0; w.part = 0; return true; }
+  const int v = u - p.full_tiles;
+  if (v >= p.tail * p.split) return false;
+  const int part = v / p.tail;
+  w.tile = p.full_tiles + v % p.tail;
+  w.kb0 = (int)((long long)kblocks * part / p.split);
+  w.kb1 = (int)((long long)kblocks * (part + 1) / p.split);
+  w.partial = p.split > 1;
+  w.part = part;
+  return true;
+}
 
 ZTB_DEVINL void decode_tile(int t, const GemmParams& p, int& mb, int& nb) {
   int per_group = GROUP_M * p.tiles_n;
@@ -73,6 +94,14 @@ ZTB_DEVINL void umma_commit_2sm(uint64_t* bar) {  // arrives on `bar` in BOTH CT
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"((uint16_t)3)
                : "memory");
+}
+ZTB_DEVINL int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+ZTB_DEVINL void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 ZTB_DEVINL void mbar_arrive_cta0(uint64_t* bar) {  // arrive on CTA 0's copy of `bar`
   uint32_t remote;
@@ -127,11 +156,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===================================================== TMA producer (both CTAs)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = pair; t < p.num_tiles; t += num_pairs) {
-        int mb, nb; decode_tile(t, p, mb, nb);
+      Unit w;
+      for (int u = pair; get_unit(u, p, kblocks, w); u += num_pairs) {
+        int mb, nb; decode_tile(w.tile, p, mb, nb);
         const int m0 = mb * TILE_M + cta_rank * BM;        // this CTA's A rows
         const int nrow0 = nb * BN + cta_rank * 128;        // this CTA's B rows
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (leader) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
           uint8_t* a = smA + stage * A_STAGE_BYTES;
@@ -158,11 +188,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = pair; t < p.num_tiles; t += num_pairs) {
+      Unit w;
+      for (int u = pair; get_unit(u, p, kblocks, w); u += num_pairs) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(smA + stage * A_STAGE_BYTES);
@@ -173,10 +204,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                : make_smem_desc(a_addr + k * 32, 16, 1024, kSwizzle128B);
             uint64_t db = B_MN ? make_smem_desc(b_addr + k * 2048, 8192, 1024, kSwizzle128B)
                                : make_smem_desc(b_addr + k * 32, 16, 1024, kSwizzle128B);
-            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb != w.kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit_2sm(&empty[stage]);
-          if (kb == kblocks - 1) umma_commit_2sm(&tfull[acc]);
+          if (kb == w.kb1 - 1) umma_commit_2sm(&tfull[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
@@ -197,12 +228,25 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     auto arrive_tempty = [&](int a) { if (leader) mbar_arrive(&tempty[a]); else mbar_arrive_cta0(&tempty[a]); };
     int acc = 0; uint32_t acc_phase = 0;
     int cbuf = 0;
-    for (int t = pair; t < p.num_tiles; t += num_pairs) {
-      int mb, nb; decode_tile(t, p, mb, nb);
+    Unit w;
+    for (int u = pair; get_unit(u, p, kblocks, w); u += num_pairs) {
+      int mb, nb; decode_tile(w.tile, p, mb, nb);
       const int m0 = mb * TILE_M + cta_rank * BM, n0 = nb * BN;
+      const bool reduce_c = p.accumulate || w.partial;
+      // K-ranges of a split tile are added into C in K order, so the bf16/fp32 sum is reproducible run to
+      // run: this warp's region of range `part` waits for the same region of range part - 1 (finished by a
+      // different CTA pair, in the same or the previous round -- every CTA is resident, so this cannot deadlock).
+      int* chain = w.partial ? p.chain + ((w.tile - p.full_tiles) * 16 + (int)cta_rank * 8 + e) : nullptr;
       const int grow = m0 + row;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after_sync();
+      if (chain != nullptr && w.part > 0) {
+        if (lane == 0) {
+          while (ld_acquire_gpu(chain) < w.part) __nanosleep(32);
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
+        __syncwarp();
+      }
       const uint32_t t_acc = tmem_base + lane_addr + acc * BN;
       // One staging buffer holds 128 B per row: 64 bf16 columns or 32 fp32 columns.  Buffers
       // alternate; before overwriting one, the issuing thread waits until at most one bulk store
@@ -218,7 +262,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         __syncwarp();
         if (lane == 0) {
           const uint8_t* src = wbuf + cbuf * WBUF_BYTES;
-          if (p.accumulate) tma_reduce_add_2d(tm, src, col, m0 + ew * 32);
+          if (reduce_c) tma_reduce_add_2d(tm, src, col, m0 + ew * 32);
           else tma_store_2d(tm, src, col, m0 + ew * 32);
           tma_commit_group();
         }
@@ -305,6 +349,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           end_buffer(&tmC, gcol);
         }
       }
+      if (chain != nullptr && w.part + 1 < p.split && lane == 0) {
+        tma_wait_group<0>();            // this range's reduce-adds have been performed ...
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        st_release_gpu(chain, w.part + 1);  // ... the next range of this region may go
+      }
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
     if (lane == 0) tma_wait_group<0>();
@@ -377,7 +426,35 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
   p.rng = g->rng; p.op_id = g->op_id;
   p.tiles_m = (g->M + TILE_M - 1) / TILE_M; p.tiles_n = (g->N + BN - 1) / BN; p.num_tiles = p.tiles_m * p.tiles_n;
   int pairs = sms / 2;
-  if (p.num_tiles < pairs) pairs = p.num_tiles;
+  // Wave quantisation: num_tiles is rarely a multiple of the 74 CTA pairs (weight gradients: 64 / 192 / 256
+  // tiles).  Cut each tile of the last, partial wave into `split` K-ranges so that it costs
+  // ceil(tail * split / pairs) / split of a tile time instead of a whole one.
+  const int kblocks = (g->K + BK - 1) / BK;
+  p.full_tiles = p.num_tiles / pairs * pairs; p.tail = p.num_tiles - p.full_tiles; p.split = 1;
+  if (p.tail > 0 && g->epilogue == ZTB_EPI_NONE && !g->no_split) {
+    float best = 1.f;
+    for (int sp = 2; sp <= 8 && kblocks / sp >= 16; ++sp) {
+      float cost = (float)((p.tail * sp + pairs - 1) / pairs) / sp + 0.03f * (sp - 1);  // + per-unit epilogue/ramp overhead (measured: 8-way split of a 64-tile problem gains nothing)
+      if (cost < best - 1e-6f) { best = cost; p.split = sp; }
+    }
+    if (p.split > 1 && !g->accumulate)   // partial sums meet in C through reduce-adds: start from zero
+      ZTB_CUDA_CHECK(cudaMemset2DAsync(g->C, (size_t)g->ldc * (g->c_is_fp32 ? 4 : 2), 0, (size_t)g->N * (g->c_is_fp32 ? 4 : 2), g->M, st));
+  }
+  p.chain = nullptr;
+  if (p.split > 1) {
+    // ordering counters: one slot of a small per-device ring per launch, zeroed in-stream
+    constexpr int kSlotInts = 128 * 16, kSlots = 64;
+    static int* ring[16] = {nullptr};
+    static unsigned next_slot = 0;
+    int dev = 0;
+    ZTB_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) { ztb_set_error("ztb_gemm_2cta", "device index out of range", __FILE__, __LINE__); return -1; }
+    if (ring[dev] == nullptr) ZTB_CUDA_CHECK(cudaMalloc(&ring[dev], sizeof(int) * kSlotInts * kSlots));
+    p.chain = ring[dev] + (size_t)(next_slot++ % kSlots) * kSlotInts;
+    ZTB_CUDA_CHECK(cudaMemsetAsync(p.chain, 0, sizeof(int) * p.tail * 16, st));
+  }
+  const int units = p.full_tiles + p.tail * p.split;
+  if (units < pairs) pairs = units;
   int grid = pairs * 2;
   if (g->a_mn_major && g->b_mn_major) return launch2<true, true>(ta, tb, tc, tx, p, grid, st);
   if (g->a_mn_major) return launch2<true, false>(ta, tb, tc, tx, p, grid, st);

@@ -62,6 +62,7 @@ struct ZtbGemmArgs {
   int a_mn_major, b_mn_major;               // operand stored with M (resp. N) contiguous: A[K,M] / B[K,N]
   const ZtbAgArgs* ag;                      // non-null: gather B's remote row chunks inside the kernel
   int two_cta;                              // use the cta_group::2 (256x256 per CTA pair) kernel
+  int no_split;                             // two_cta: disable K-splitting of the last partial wave
 };
 int ztb_gemm_2cta(const ZtbGemmArgs* args, int sms, cudaStream_t st);
 int ztb_gemm(const ZtbGemmArgs* args, int sms, cudaStream_t st);
