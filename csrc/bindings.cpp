@@ -19,6 +19,12 @@ int num_sms() {
   if (!n) n = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   return n;
 }
+// SMs that persistent GEMMs leave free for a concurrently running side kernel (fused reduce-scatter + AdamW)
+int g_sm_reserve = 0;
+int gemm_sms() {
+  int n = num_sms() - g_sm_reserve;
+  return n < 2 ? 2 : n;
+}
 void need(bool c, const char* msg) {
   if (!c) throw std::invalid_argument(msg);
 }
@@ -156,7 +162,7 @@ at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tens
     a.rng = (const uint64_t*)rng->data_ptr<int64_t>();
   }
   need(epilogue != ZTB_EPI_DROPOUT_ADD || a.rng != nullptr, "gemm: dropout epilogue needs rng");
-  check(ztb_gemm(&a, num_sms(), stream()), "gemm");
+  check(ztb_gemm(&a, gemm_sms(), stream()), "gemm");
   return C;
 }
 
@@ -182,7 +188,7 @@ at::Tensor gemm_ag(const at::Tensor& A, const at::Tensor& B, std::vector<int64_t
   a.M = A.size(0); a.K = A.size(1); a.N = B.size(0);
   a.lda = A.stride(0); a.ldb = B.stride(0); a.ldc = C.stride(0);
   a.ag = &ag;
-  check(ztb_gemm(&a, num_sms(), stream()), "gemm_ag");
+  check(ztb_gemm(&a, gemm_sms(), stream()), "gemm_ag");
   return C;
 }
 
@@ -190,7 +196,7 @@ at::Tensor gemm_ag(const at::Tensor& A, const at::Tensor& B, std::vector<int64_t
 // peer's flat gradient buffer (first = local).  segs: uint8 CUDA tensor of packed ZtbSegment.
 void adamw_shard(at::Tensor& master, at::Tensor& m, at::Tensor& v, at::Tensor& flat_param, std::vector<int64_t> grad_ptrs,
                  bool grad_is_fp32, const at::Tensor& segs, int64_t nseg, int64_t total_tiles, double lr, double beta1, double beta2,
-                 double eps, double wd, double clip, double grad_scale, int64_t step, int64_t wait_flags_ptr, int64_t wait_value) {
+                 double eps, double wd, double clip, double grad_scale, int64_t step, int64_t wait_flags_ptr, int64_t wait_value, int64_t side_sms) {
   need(master.is_cuda() && master.scalar_type() == at::kFloat && m.scalar_type() == at::kFloat && v.scalar_type() == at::kFloat, "adamw_shard: fp32 state");
   need(is_bf16_cuda(flat_param), "adamw_shard: bf16 flat_param");
   need(segs.is_cuda() && segs.scalar_type() == at::kByte && segs.numel() >= (int64_t)(nseg * sizeof(ZtbSegment)), "adamw_shard: segs");
@@ -204,7 +210,7 @@ void adamw_shard(at::Tensor& master, at::Tensor& m, at::Tensor& v, at::Tensor& f
   a.bc2 = (float)(1.0 - std::pow(beta2, (double)step));
   check(ztb_adamw_shard(master.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), flat_param.data_ptr(), gp.data(), (int)gp.size(),
                         grad_is_fp32, reinterpret_cast<const ZtbSegment*>(segs.data_ptr()), (int)nseg, total_tiles, a,
-                        reinterpret_cast<const int*>(wait_flags_ptr), (int)wait_value, num_sms(), stream()), "adamw_shard");
+                        reinterpret_cast<const int*>(wait_flags_ptr), (int)wait_value, num_sms(), (int)side_sms, stream()), "adamw_shard");
 }
 
 int64_t segment_struct_size() { return sizeof(ZtbSegment); }
@@ -296,7 +302,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("aux_out") = py::none(), py::arg("p") = 0.0, py::arg("rng") = py::none(), py::arg("op_id") = 0,
         py::arg("accumulate") = false, py::arg("a_mn") = false, py::arg("b_mn") = false, py::arg("two_cta") = false, py::arg("no_split") = false);
   m.def("gemm_ag", &gemm_ag);
-  m.def("adamw_shard", &adamw_shard);
+  m.def("adamw_shard", &adamw_shard, py::arg("master"), py::arg("m"), py::arg("v"), py::arg("flat_param"), py::arg("grad_ptrs"),
+        py::arg("grad_is_fp32"), py::arg("segs"), py::arg("nseg"), py::arg("total_tiles"), py::arg("lr"), py::arg("beta1"), py::arg("beta2"),
+        py::arg("eps"), py::arg("wd"), py::arg("clip"), py::arg("grad_scale"), py::arg("step"), py::arg("wait_flags_ptr") = 0,
+        py::arg("wait_value") = 0, py::arg("side_sms") = 0);
+  m.def("set_sm_reserve", [](int64_t n) { g_sm_reserve = n < 0 ? 0 : (int)n; }, "persistent GEMMs leave this many SMs free");
+  m.def("get_sm_reserve", []() { return (int64_t)g_sm_reserve; });
   m.def("segment_struct_size", &segment_struct_size);
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_bwd", &attention_bwd, py::arg("qkv"), py::arg("out"), py::arg("dout"), py::arg("lse"), py::arg("slopes"), py::arg("H"),

@@ -32,8 +32,12 @@ ZTB_DEVINL uint32_t ld_acquire_sys(const int* p) {
   return v;
 }
 
-template <bool kGradFp32>
-__global__ void __launch_bounds__(kAdamThreads) adamw_shard_kernel(float* __restrict__ master, float* __restrict__ m,
+// kThreads == kAdamThreads: the wide form, many small CTAs filling the GPU.
+// kThreads == 1024: the "side" form -- a handful of CTAs (launched as clusters of 2, one CTA per SM) that own a
+// few SMs for the whole update while persistent GEMMs, sized to leave exactly those SMs free, keep the rest.
+// A 1024-thread CTA behaves as 8 virtual 128-thread CTAs.
+template <bool kGradFp32, int kThreads>
+__global__ void __launch_bounds__(kThreads) adamw_shard_kernel(float* __restrict__ master, float* __restrict__ m,
                                                                    float* __restrict__ v, bf16* __restrict__ flat_param,
                                                                    PeerPtrs peers, int n_peers,
                                                                    const ZtbSegment* __restrict__ segs, int nseg,
@@ -47,14 +51,17 @@ __global__ void __launch_bounds__(kAdamThreads) adamw_shard_kernel(float* __rest
     }
     __syncthreads();
   }
-  for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+  constexpr int kSub = kThreads / kAdamThreads;
+  const int vlane = threadIdx.x % kAdamThreads;
+  const long long vblock = (long long)blockIdx.x * kSub + threadIdx.x / kAdamThreads, vgrid = (long long)gridDim.x * kSub;
+  for (long long t = vblock; t < total_tiles; t += vgrid) {
     int lo = 0, hi = nseg - 1;  // last segment with tile_begin <= t
     while (lo < hi) {
       int mid = (lo + hi + 1) >> 1;
       if (segs[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
     }
     const ZtbSegment sg = segs[lo];
-    long long e0 = (t - sg.tile_begin) * kAdamTile + (long long)threadIdx.x * kAdamVec;
+    long long e0 = (t - sg.tile_begin) * kAdamTile + (long long)vlane * kAdamVec;
     if (e0 >= sg.len) continue;  // len is a multiple of 8 (chunks are 64-element aligned)
     long long fo = sg.flat_off + e0, so = sg.shard_off + e0;
     float g[8];
@@ -100,19 +107,52 @@ __global__ void __launch_bounds__(kAdamThreads) adamw_shard_kernel(float* __rest
 
 using namespace ztb;
 
+constexpr int kSideThreads = 1024;
+constexpr int kSideSmem = 120 * 1024;   // more than half an SM's shared memory: one side CTA per SM
+
+template <bool kGradFp32>
+static int launch_side(float* master, float* m, float* v, bf16* flat_param, const PeerPtrs& pp, int n_peers, const ZtbSegment* segs,
+                       int nseg, long long total_tiles, const ZtbAdamArgs& a, const int* wait_flags, int wait_value, int ctas,
+                       cudaStream_t st) {
+  auto kern = adamw_shard_kernel<kGradFp32, kSideThreads>;
+  static bool configured = false;
+  if (!configured) {
+    ZTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSideSmem));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas, 1, 1);
+  cfg.blockDim = dim3(kSideThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSideSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;   // a pair lands on one TPC: the same granularity the 2-CTA GEMM needs
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  ZTB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, master, m, v, flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value));
+  return 0;
+}
+
+// side_sms > 0: run on exactly that many SMs (rounded down to an even number, >= 2) next to concurrently running
+// persistent kernels instead of spreading over the whole GPU.
 int ztb_adamw_shard(float* master, float* m, float* v, void* flat_param, const void* const* grads, int n_peers,
                     int grad_is_fp32, const ZtbSegment* segs, int nseg, long long total_tiles, ZtbAdamArgs a,
-                    const int* wait_flags, int wait_value, int sms, cudaStream_t st) {
+                    const int* wait_flags, int wait_value, int sms, int side_sms, cudaStream_t st) {
   if (n_peers < 1 || n_peers > kMaxPeers) { ztb_set_error("adamw_shard", "n_peers out of range", __FILE__, __LINE__); return -1; }
   if (total_tiles <= 0) return 0;
   PeerPtrs pp;
   for (int i = 0; i < kMaxPeers; ++i) pp.g[i] = i < n_peers ? grads[i] : nullptr;
+  if (side_sms > 0) {
+    int ctas = side_sms < 2 ? 2 : (side_sms & ~1);
+    return grad_is_fp32 ? launch_side<true>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value, ctas, st)
+                        : launch_side<false>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value, ctas, st);
+  }
   long long want = total_tiles < (long long)sms * 16 ? total_tiles : (long long)sms * 16;
   int grid = (int)want;
   if (grad_is_fp32)
-    adamw_shard_kernel<true><<<grid, kAdamThreads, 0, st>>>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value);
+    adamw_shard_kernel<true, kAdamThreads><<<grid, kAdamThreads, 0, st>>>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value);
   else
-    adamw_shard_kernel<false><<<grid, kAdamThreads, 0, st>>>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value);
+    adamw_shard_kernel<false, kAdamThreads><<<grid, kAdamThreads, 0, st>>>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

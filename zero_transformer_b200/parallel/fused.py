@@ -143,7 +143,7 @@ class FusedComm:
     def begin_step(self) -> None:
         self.epoch += 1
 
-    def bucket_update(self, b: int, *, master, m, v, lr, beta1, beta2, eps, wd, step, clip, grad_scale) -> None:
+    def bucket_update(self, b: int, *, master, m, v, lr, beta1, beta2, eps, wd, step, clip, grad_scale, side_sms: int = 0) -> None:
         """Bucket ``b``'s gradients are final on the current (compute) stream: reduce-scatter them
         from every peer, apply AdamW to the owned shard and publish the new bf16 chunk."""
         e = self.epoch
@@ -156,7 +156,7 @@ class FusedComm:
                 self._C.wait_flags(self._my_row(FLAG_GRAD_READY, b), self.world, e)
             segs, n, tiles = self.adam[b]
             self._C.adamw_shard(master, m, v, self.flat_param, self.grad_ptrs if self.world > 1 else self._grad.ptrs,
-                                self.grad_fp32, segs, n, tiles, lr, beta1, beta2, eps, wd, clip, grad_scale, step, 0, 0)
+                                self.grad_fp32, segs, n, tiles, lr, beta1, beta2, eps, wd, clip, grad_scale, step, 0, 0, side_sms)
             if self.world > 1:
                 self._signal(FLAG_SHARD_READY, b, e)
             else:

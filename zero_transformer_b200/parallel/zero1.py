@@ -27,7 +27,7 @@ communication buffer (no copy-in), and ``step()`` never walks Python lists of
 tensors on the hot path.
 """
 from __future__ import annotations
-
+import os
 import math
 from typing import Callable, Dict, Optional
 
@@ -62,11 +62,25 @@ class Zero1Engine:
         decay_mask: Optional[Dict[str, bool]] = None,
         bucket_of=default_bucket_of,
         ag_gemm: bool = True,
+        comm_sms="auto",
     ):
         self.model = model
         self.group = group
         self.ag_gemm = bool(ag_gemm)
         self.rank, self.world = _dist_info(group)
+        # SMs handed to the per-bucket reduce-scatter+AdamW kernels while the last micro-batch's backward
+        # runs (its persistent GEMMs shrink by as many).  A GEMM CTA needs a whole SM, so without a
+        # reservation the update kernel and the GEMMs alternate (each bucket's update runs between two
+        # GEMMs at full HBM bandwidth).  Measured on 1 GPU / 1.3B (bench.py, ms per step): 0 -> 263,
+        # 12 -> 268, 8 -> 289, 4 -> 369: one SM streams only ~45 GB/s, so a reservation large enough to keep
+        # up costs the GEMMs more than the alternation does.  "auto" therefore means 0; the knob is kept
+        # for larger worlds, where the per-rank update is 1/world of this.
+        env_sms = os.environ.get("ZTB_COMM_SMS")
+        if env_sms is not None:
+            comm_sms = int(env_sms)
+        elif comm_sms in ("auto", None):
+            comm_sms = 0
+        self.comm_sms = max(0, int(comm_sms)) & ~1
         self.lr_fn = lr_fn
         self.weight_decay = float(weight_decay)
         self.beta1, self.beta2 = float(betas[0]), float(betas[1])
@@ -159,7 +173,7 @@ class Zero1Engine:
             return
         b = self._block_bucket.get(i)
         if b is not None and b not in self._updated:
-            self._fused.bucket_update(b, **self._adam_kwargs())
+            self._fused.bucket_update(b, side_sms=self.comm_sms, **self._adam_kwargs())
             self._updated.add(b)
 
     def _on_block_forward_pre(self, i: int) -> None:
@@ -203,9 +217,14 @@ class Zero1Engine:
             self._fused.begin_step()
         self._in_engine_backward = True
         K.GRAD_MODE["accumulate"] = not self._overwrite_next
+        reserve = self.comm_sms if last else 0
+        if reserve:
+            K._C.set_sm_reserve(reserve)
         try:
             loss.backward()
         finally:
+            if reserve:
+                K._C.set_sm_reserve(0)
             K.GRAD_MODE["accumulate"] = True
             self._in_engine_backward = False
         self._overwrite_next = False

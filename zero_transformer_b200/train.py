@@ -81,6 +81,7 @@ class Trainer:
             compute_dtype=torch.bfloat16 if on_gpu else torch.float32,
             grad_dtype=(gd if on_gpu else torch.float32),
             ag_gemm=bool(t.get("ag_gemm", True)),
+            comm_sms=t.get("comm_sms", "auto"),
         )
         self.log.debug(self.engine.memory_report())
         self.log.debug("model %s: %.1fM parameters; optimizer state sharded over %d rank(s); params/grads/activations replicated",
