@@ -284,7 +284,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       uint8_t* prow = smP + hf * 16384 + r * 128;
 #pragma unroll
       for (int c16 = 0; c16 < 8; ++c16)
-        *reinterpret_cast<uint4*>(prow + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[c16 * 4], pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]);
+        sts_v4(prow + ((c16 ^ (r & 7)) << 4), make_uint4(pk[c16 * 4], pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]));
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(p_ready);
@@ -313,7 +313,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if ((col >> 6) < FULLCH) {
         uint8_t* orow = smP + (col >> 6) * 16384 + r * 128;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(orow + (((((col & 63) >> 3) + q4) ^ (r & 7)) << 4)) = o4[q4];
+        for (int q4 = 0; q4 < 4; ++q4) sts_v4(orow + (((((col & 63) >> 3) + q4) ^ (r & 7)) << 4), o4[q4]);
       } else {  // partial chunk (head_dim 96): straight to global, 64 contiguous bytes per row
         bf16* gp = p.out + (size_t)(row0 + r) * D + colQ + col;
 #pragma unroll
@@ -543,7 +543,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       uint8_t* prow = smP + r * 128;
 #pragma unroll
       for (int c16 = 0; c16 < 8; ++c16)
-        *reinterpret_cast<uint4*>(prow + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[c16 * 4], pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]);
+        sts_v4(prow + ((c16 ^ (r & 7)) << 4), make_uint4(pk[c16 * 4], pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]));
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(p_ready);
@@ -564,7 +564,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                               pack_bf16(__uint_as_float(o[q4 * 8 + 2]) * inv, __uint_as_float(o[q4 * 8 + 3]) * inv),
                               pack_bf16(__uint_as_float(o[q4 * 8 + 4]) * inv, __uint_as_float(o[q4 * 8 + 5]) * inv),
                               pack_bf16(__uint_as_float(o[q4 * 8 + 6]) * inv, __uint_as_float(o[q4 * 8 + 7]) * inv));
-        *reinterpret_cast<uint4*>(orow + ((((c & 1) * 4 + q4) ^ (r & 7)) << 4)) = o4;
+        sts_v4(orow + ((((c & 1) * 4 + q4) ^ (r & 7)) << 4), o4);
       }
     }
     p.lse[(size_t)bh * p.T + qi] = (m + log2f(l)) * 0.6931471805599453f;
@@ -789,8 +789,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           for (int e = 0; e < 8; ++e) pk[e] = pack_bf16(s[g * 16 + 2 * e], s[g * 16 + 2 * e + 1]);
         }
         const int c16 = g * 2;
-        *reinterpret_cast<uint4*>(prow + (c16 >> 3) * 16384 + (((c16 & 7) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(prow + ((c16 + 1) >> 3) * 16384 + ((((c16 + 1) & 7) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        sts_v4(prow + (c16 >> 3) * 16384 + (((c16 & 7) ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        sts_v4(prow + ((c16 + 1) >> 3) * 16384 + ((((c16 + 1) & 7) ^ (r & 7)) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
@@ -812,7 +812,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                               pack_bf16(__uint_as_float(o[q4 * 8 + 2]) * inv, __uint_as_float(o[q4 * 8 + 3]) * inv),
                               pack_bf16(__uint_as_float(o[q4 * 8 + 4]) * inv, __uint_as_float(o[q4 * 8 + 5]) * inv),
                               pack_bf16(__uint_as_float(o[q4 * 8 + 6]) * inv, __uint_as_float(o[q4 * 8 + 7]) * inv));
-        *reinterpret_cast<uint4*>(orow + ((((c & 1) * 4 + q4) ^ (r & 7)) << 4)) = o4;
+        sts_v4(orow + ((((c & 1) * 4 + q4) ^ (r & 7)) << 4), o4);
       }
     }
     p.lse[(size_t)bh * p.T + qi] = (m + log2f(l)) * 0.6931471805599453f;
@@ -1032,13 +1032,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int kv0 = jb * ATT_BN + hf * 64;
     const int cmax = r - hf * 64;
     uint8_t* stage = hf == 0 ? smP : smDS;   // dQ staging: half 0 -> P buffer, half 1 -> dS buffer
+    // the per-row statistics of iteration it + 1 are fetched during iteration it (an L2 round trip is ~700 cycles,
+    // which would otherwise sit in front of every P phase)
+    float lse_nxt = p.lse[(size_t)bh * p.T + jb * ATT_BM + r];
+    float delta_nxt = p.delta[(size_t)bh * p.T + jb * ATT_BM + r];
     for (int it = 0; it < niter; ++it) {
       const uint32_t phs = it & 1;
       const int qb = jb + it;
       const int qi = qb * ATT_BM + r;
       const size_t ridx = (size_t)bh * p.T + qi;
-      const float lse2 = p.lse[ridx] * 1.4426950408889634f;
-      const float delta = p.delta[ridx];
+      const float lse2 = lse_nxt * 1.4426950408889634f;
+      const float delta = delta_nxt;
+      if (it + 1 < niter) {
+        lse_nxt = p.lse[ridx + ATT_BM];
+        delta_nxt = p.delta[ridx + ATT_BM];
+      }
       const float kscale = keep_scale * p.scale, ndelta = -delta * p.scale;
       const uint64_t row_id = (uint64_t)bh * p.T + qi;
       // ---- P = exp2(S*c + alibi - lse)
@@ -1100,7 +1108,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             const int c = c16 * 8 + e * 2;
             pk[e] = pack_bf16(fmaxf(s[c], 0.f), fmaxf(s[c + 1], 0.f));
           }
-          *reinterpret_cast<uint4*>(prow + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          sts_v4(prow + ((c16 ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
         }
       }
       fence_proxy_async_smem();
@@ -1131,7 +1139,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
               pk[e] = pack_bf16(fabsf(s0) * d0, fabsf(s1) * d1);
             }
             const int c16 = c32 * 4 + q4;
-            *reinterpret_cast<uint4*>(drow + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            sts_v4(drow + ((c16 ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
           }
         }
       }
@@ -1155,7 +1163,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         uint8_t* orow = stage + c32 * 16384 + r * 128;
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4)
-          *reinterpret_cast<uint4*>(orow + ((q4 ^ (r & 7)) << 4)) = make_uint4(o[q4 * 4], o[q4 * 4 + 1], o[q4 * 4 + 2], o[q4 * 4 + 3]);
+          sts_v4(orow + ((q4 ^ (r & 7)) << 4), make_uint4(o[q4 * 4], o[q4 * 4 + 1], o[q4 * 4 + 2], o[q4 * 4 + 3]));
       }
       tc_fence_before_sync();
       mbar_arrive(dq_drained);
@@ -1209,7 +1217,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         if ((col >> 6) < FULLCH) {
           uint8_t* orow = stg + (col >> 6) * 16384 + r * 128;
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(orow + (((((col & 63) >> 3) + q4) ^ (r & 7)) << 4)) = o4[q4];
+          for (int q4 = 0; q4 < 4; ++q4) sts_v4(orow + (((((col & 63) >> 3) + q4) ^ (r & 7)) << 4), o4[q4]);
         } else {
           bf16* gp = p.dqkv + (size_t)(krow + r) * (3 * D) + gcol0 + col;
 #pragma unroll

@@ -166,6 +166,12 @@ ZTB_DEVINL void tma_reduce_add_2d(const void* tmap, const void* smem_src, int c0
                : "memory");
 }
 ZTB_DEVINL void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// 16-byte store to shared memory through the shared window (pointers derived from the aligned dynamic smem base
+// lose their address space, and the compiler would otherwise emit generic ST.E.128)
+ZTB_DEVINL void sts_v4(void* p, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 template <int N>
 ZTB_DEVINL void tma_wait_group_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");

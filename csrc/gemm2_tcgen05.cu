@@ -274,7 +274,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int j = 0; j < 8; ++j) {
           uint4 o = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-          *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
+          sts_v4(rowp + ((j ^ (row & 7)) << 4), o);
         }
       };
 #pragma unroll 1
@@ -339,7 +339,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int j = 0; j < 8; ++j) {
               const float* s4 = v + h * 32 + 4 * j;
               uint4 o = make_uint4(__float_as_uint(s4[0]), __float_as_uint(s4[1]), __float_as_uint(s4[2]), __float_as_uint(s4[3]));
-              *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
+              sts_v4(rowp + ((j ^ (row & 7)) << 4), o);
             }
             end_buffer(&tmC, gcol + h * 32);
           }
