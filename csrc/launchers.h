@@ -33,6 +33,7 @@ struct ZtbSegment {      // one parameter region's chunk owned by this rank
 };
 struct ZtbAdamArgs {
   float lr, beta1, beta2, eps, wd, clip, grad_scale, bc1, bc2;
+  const float* scale_mul;   // optional device scalar multiplied into grad_scale (global-norm clip coefficient)
 };
 // grads[p] = flat grad buffer of peer p (p = 0 is local); n_peers == 1 -> plain fused AdamW.
 int ztb_adamw_shard(float* master, float* m, float* v, void* flat_param, const void* const* grads, int n_peers,

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(kThreads) adamw_shard_kernel(float* __restrict
     }
     __syncthreads();
   }
+  const float gscale = a.scale_mul != nullptr ? a.grad_scale * __ldg(a.scale_mul) : a.grad_scale;
   constexpr int kSub = kThreads / kAdamThreads;
   const int vlane = threadIdx.x % kAdamThreads;
   const long long vblock = (long long)blockIdx.x * kSub + threadIdx.x / kAdamThreads, vgrid = (long long)gridDim.x * kSub;
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(kThreads) adamw_shard_kernel(float* __restrict
     const float wd = sg.decay ? a.wd : 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float gg = g[k] * a.grad_scale;
+      float gg = g[k] * gscale;
       if (a.clip > 0.f) gg = fminf(fmaxf(gg, -a.clip), a.clip);
       float mk = a.beta1 * mf[k] + (1.f - a.beta1) * gg;
       float vk = a.beta2 * vf[k] + (1.f - a.beta2) * gg * gg;

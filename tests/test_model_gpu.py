@@ -115,6 +115,37 @@ def test_overlapped_engine_backward_matches_plain_path():
     assert rel < 5e-3, rel.item()  # embedding-gradient atomics are order-nondeterministic; Adam amplifies near-zero grads
 
 
+def test_fused_global_norm_clip_matches_plain_adamw():
+    """Two-phase fused update (clip_mode=global_norm) on one GPU against the fp32 PlainAdamW oracle."""
+    from zero_transformer_b200.optim.schedule import WarmupCosine
+    from zero_transformer_b200.parallel.zero1 import PlainAdamW, Zero1Engine
+
+    lr_fn = WarmupCosine(1e-3, 0, 100, 1e-4)
+    m, ref, cfg = _models(dropout=0.0)
+    m = m.float()
+    ref.load_state_dict(m.state_dict())   # the oracle starts from the same (bf16-representable) weights
+    eng = Zero1Engine(m, lr_fn=lr_fn, backend="fused", grad_accum_steps=2, clip_mode="global_norm", clip=0.05)
+    x = torch.randint(0, cfg.vocab_size, (8, 256), dtype=torch.int32).cuda()
+    eng.zero_grad(lazy=True)
+    for k, mb in enumerate(x.chunk(2)):
+        eng.backward(m.loss(mb, train=False), last=(k == 1))
+    grads = {n: p.grad.detach().float().clone() for n, p in m.named_parameters()}
+    eng.step()
+    eng.synchronize()
+    gnorm = torch.sqrt(sum(g.pow(2).sum() for g in grads.values())) * 0.5
+    assert gnorm > 0.05   # the clip is active
+    torch.testing.assert_close(eng.last_grad_norm.reshape(()), gnorm, rtol=1e-3, atol=0)
+    # oracle: same bf16 gradients through the unsharded fp32 AdamW
+    for (n, p) in ref.named_parameters():
+        p.grad = grads[n]
+    opt = PlainAdamW(ref, lr_fn=lr_fn, grad_accum_steps=2, clip_mode="global_norm", clip=0.05)
+    opt.step()
+    st = eng.consolidated_state(0)
+    for n in opt.master:
+        torch.testing.assert_close(st["exp_avg"][n].cuda(), opt.m[n], rtol=2e-3, atol=1e-9, msg=n)
+        torch.testing.assert_close(st["params"][n].cuda(), opt.master[n], rtol=1e-4, atol=1e-6, msg=n)
+
+
 def test_backward_is_bitwise_reproducible():
     """Two identical forward/backward passes give bit-identical block gradients: the K-split GEMM tail
     (gemm2_tcgen05.cu) reduces its partial sums in a fixed order.  T = 256 keeps the attention dQ

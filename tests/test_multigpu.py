@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, backend, out):
+def _worker(rank, world, port, backend, out, clip_mode="elementwise", clip=1.0):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -33,7 +33,7 @@ def _worker(rank, world, port, backend, out):
         torch.manual_seed(0)
         with torch.device("cuda"):
             model = Transformer(GPTConfig(**CFG))
-        eng = Zero1Engine(model, lr_fn=WarmupCosine(1e-3, 0, 100, 1e-4), grad_accum_steps=2, backend=backend)
+        eng = Zero1Engine(model, lr_fn=WarmupCosine(1e-3, 0, 100, 1e-4), grad_accum_steps=2, backend=backend, clip_mode=clip_mode, clip=clip)
         init = eng.consolidated_state(0)
         g = torch.Generator().manual_seed(1)
         losses = []
@@ -63,9 +63,9 @@ def _worker(rank, world, port, backend, out):
         dist.destroy_process_group()
 
 
-def _run(backend, tmp_path, world=2):
-    out = str(tmp_path / f"{backend}.pt")
-    mp.spawn(_worker, args=(world, _free_port(), backend, out), nprocs=world, join=True)
+def _run(backend, tmp_path, world=2, clip_mode="elementwise", clip=1.0):
+    out = str(tmp_path / f"{backend}_{clip_mode}.pt")
+    mp.spawn(_worker, args=(world, _free_port(), backend, out, clip_mode, clip), nprocs=world, join=True)
     return torch.load(out, weights_only=False)
 
 
@@ -79,5 +79,18 @@ def test_fused_backend_matches_nccl_backend(tmp_path):
     for n in a["params"]:
         da, db = a["params"][n] - a["init"][n], b["params"][n] - b["init"][n]
         assert torch.equal(a["init"][n], b["init"][n])
+        rel = (da - db).norm() / (db.norm() + 1e-12)
+        assert rel < 0.15, (n, rel.item())
+
+
+def test_fused_two_phase_global_norm_matches_nccl_backend(tmp_path):
+    """clip_mode=global_norm on the fused backend: in-place P2P reduce-scatter per bucket (overlapped with
+    backward), one scalar all-reduce, then AdamW on the reduced chunks with the device-side coefficient."""
+    a = _run("fused", tmp_path, clip_mode="global_norm", clip=0.05)
+    b = _run("nccl", tmp_path, clip_mode="global_norm", clip=0.05)
+    assert a["same"] and b["same"]
+    assert a["losses"] == pytest.approx(b["losses"], rel=2e-2)
+    for n in a["params"]:
+        da, db = a["params"][n] - a["init"][n], b["params"][n] - b["init"][n]
         rel = (da - db).norm() / (db.norm() + 1e-12)
         assert rel < 0.15, (n, rel.item())

@@ -77,13 +77,13 @@ def test_single_rank_engine_matches_plain_adamw(backend):
     assert eng.step_count == 4 and eng.lr == pytest.approx(LR(4))
 
 
-def _worker(rank, world, port, backend, q):
+def _worker(rank, world, port, backend, q, clip_mode="elementwise", clip=1.0):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.manual_seed(0)
         model = Transformer(GPTConfig(**CFG))
-        eng = Zero1Engine(model, lr_fn=LR, grad_accum_steps=2, backend=backend)
+        eng = Zero1Engine(model, lr_fn=LR, grad_accum_steps=2, backend=backend, clip_mode=clip_mode, clip=clip)
         g = torch.Generator().manual_seed(1)
         batches = [torch.randint(0, 128, (4 * world, 32), generator=g) for _ in range(3)]
         for b in batches:
@@ -99,14 +99,16 @@ def _worker(rank, world, port, backend, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("backend", ["nccl", "allreduce"])
-def test_world2_gloo_matches_single_process(backend, tmp_path):
-    """2 ranks x 2 micro-batches x 2 rows == 1 process x 2 micro-batches x 4 rows."""
+@pytest.mark.parametrize("backend,clip_mode,clip", [("nccl", "elementwise", 1.0), ("allreduce", "elementwise", 1.0),
+                                                    ("nccl", "global_norm", 0.05)])
+def test_world2_gloo_matches_single_process(backend, clip_mode, clip, tmp_path):
+    """2 ranks x 2 micro-batches x 2 rows == 1 process x 2 micro-batches x 4 rows (both clipping modes; the
+    global-norm threshold is small enough that the clip is active)."""
     world = 2
     ctx = mp.get_context("spawn")
     q = str(tmp_path / "out.pt")
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, q, clip_mode, clip)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -117,7 +119,7 @@ def test_world2_gloo_matches_single_process(backend, tmp_path):
 
     torch.manual_seed(0)
     ref = Transformer(GPTConfig(**CFG))
-    opt = PlainAdamW(ref, lr_fn=LR, grad_accum_steps=2)
+    opt = PlainAdamW(ref, lr_fn=LR, grad_accum_steps=2, clip_mode=clip_mode, clip=clip)
     g = torch.Generator().manual_seed(1)
     batches = [torch.randint(0, 128, (4 * world, 32), generator=g) for _ in range(3)]
     for b in batches:
@@ -130,6 +132,24 @@ def test_world2_gloo_matches_single_process(backend, tmp_path):
         torch.testing.assert_close(state["params"][n], opt.master[n], rtol=2e-5, atol=2e-6, msg=n)
         torch.testing.assert_close(state["exp_avg"][n], opt.m[n], rtol=2e-4, atol=1e-7, msg=n)
     assert state["step"] == 3
+
+
+def test_global_norm_clip_scales_the_whole_gradient():
+    """clip_mode=global_norm: g <- g * min(1, clip / ||g||_2) over ALL parameters (non-default option)."""
+    torch.manual_seed(0)
+    m = Transformer(GPTConfig(**CFG))
+    eng = Zero1Engine(m, lr_fn=LR, backend="nccl", clip_mode="global_norm", clip=1e-3)
+    x = torch.randint(0, 128, (4, 32))
+    eng.zero_grad()
+    m.loss(x, train=False).backward()
+    gnorm = torch.sqrt(sum(p.grad.float().pow(2).sum() for p in m.parameters()))
+    eng.step()
+    assert gnorm > 1e-3
+    torch.testing.assert_close(eng.last_grad_norm.reshape(()), gnorm, rtol=1e-5, atol=0)
+    # first Adam step: m = (1 - b1) * clipped g, so ||m|| = 0.1 * clip
+    torch.testing.assert_close(eng.exp_avg.norm(), torch.tensor(0.1 * 1e-3), rtol=1e-3, atol=0)
+    with pytest.raises(ValueError):
+        Zero1Engine(Transformer(GPTConfig(**CFG)), lr_fn=LR, backend="nccl", clip_mode="nope")
 
 
 def test_elementwise_clip_not_global_norm():

@@ -26,6 +26,7 @@ import torch.distributed as dist
 
 ADAM_TILE = 1024  # elements per CTA tile; must match kAdamTile in csrc/optim.cu
 COPY_TILE = 8192  # must match kCopyTile in csrc/comm.cu
+RS_TILE = 2048    # elements per CTA tile of csrc/comm.cu reduce_scatter_kernel
 FLAG_GRAD_READY, FLAG_SHARD_READY = 0, 1
 MAX_RANKS = 8
 
@@ -102,11 +103,16 @@ class FusedComm:
         self._grad = SymmetricBuffer(layout.total, grad_dtype, device, group, world)
         self._flags = SymmetricBuffer(2 * self.nb * MAX_RANKS, torch.int32, device, group, world)
         self.flat_param, self.flat_grad = self._param.tensor, self._grad.tensor
-        self.adam, self.pull = [], []
+        self.adam, self.pull, self.rs_inplace = [], [], []
         for b in layout.buckets:
             segs = [(r.offset + rank * r.chunk, r.shard_offset, r.chunk, int(r.decay)) for r in b.regions]
             t, tiles = pack_segments(segs, device, ADAM_TILE)
             self.adam.append((t, len(segs), tiles))
+            # stand-alone reduce-scatter that leaves the sum in place (own chunk of the local gradient buffer):
+            # the two-phase path of global-norm clipping
+            rs = [(r.offset + rank * r.chunk, r.offset + rank * r.chunk, r.chunk, 0) for r in b.regions]
+            t, tiles = pack_segments(rs, device, RS_TILE)
+            self.rs_inplace.append((t, len(rs), tiles))
             # rotated source order: at any moment every rank reads from a different owner, so no
             # owner's NVLink egress is shared by several readers
             pl = [(r.offset + p * r.chunk, 0, r.chunk, p) for p in self._peer_order(rank, world) for r in b.regions]
@@ -143,7 +149,8 @@ class FusedComm:
     def begin_step(self) -> None:
         self.epoch += 1
 
-    def bucket_update(self, b: int, *, master, m, v, lr, beta1, beta2, eps, wd, step, clip, grad_scale, side_sms: int = 0) -> None:
+    def bucket_update(self, b: int, *, master, m, v, lr, beta1, beta2, eps, wd, step, clip, grad_scale, side_sms: int = 0,
+                      reduced: bool = False, scale_mul: Optional[torch.Tensor] = None) -> None:
         """Bucket ``b``'s gradients are final on the current (compute) stream: reduce-scatter them
         from every peer, apply AdamW to the owned shard and publish the new bf16 chunk."""
         e = self.epoch
@@ -151,17 +158,34 @@ class FusedComm:
         self._ev.record(cur)
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self._ev)
-            if self.world > 1:
+            if self.world > 1 and not reduced:
                 self._signal(FLAG_GRAD_READY, b, e)
                 self._C.wait_flags(self._my_row(FLAG_GRAD_READY, b), self.world, e)
             segs, n, tiles = self.adam[b]
-            self._C.adamw_shard(master, m, v, self.flat_param, self.grad_ptrs if self.world > 1 else self._grad.ptrs,
-                                self.grad_fp32, segs, n, tiles, lr, beta1, beta2, eps, wd, clip, grad_scale, step, 0, 0, side_sms)
+            # reduced=True: bucket_reduce() already left the cross-rank sum in the local buffer
+            ptrs = self._grad.ptrs[self.rank:self.rank + 1] if (reduced or self.world == 1) else self.grad_ptrs
+            self._C.adamw_shard(master, m, v, self.flat_param, ptrs, self.grad_fp32, segs, n, tiles, lr, beta1, beta2, eps, wd, clip,
+                                grad_scale, step, 0, 0, side_sms, scale_mul.data_ptr() if scale_mul is not None else 0)
             if self.world > 1:
                 self._signal(FLAG_SHARD_READY, b, e)
             else:
                 self.ready[b].record(self.stream)
         self._pending[b] = True
+
+    def bucket_reduce(self, b: int) -> None:
+        """Phase 1 of a two-phase update (global-norm clipping): reduce-scatter bucket ``b`` over peer memory,
+        leaving the sum in this rank's own chunk of the local gradient buffer."""
+        if self.grad_fp32:
+            raise NotImplementedError("two-phase update needs bf16 gradient buffers")
+        e = self.epoch
+        self._ev.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self._ev)
+            if self.world > 1:
+                self._signal(FLAG_GRAD_READY, b, e)
+                self._C.wait_flags(self._my_row(FLAG_GRAD_READY, b), self.world, e)
+                segs, n, tiles = self.rs_inplace[b]
+                self._C.reduce_scatter(self.flat_grad, self.grad_ptrs, segs, n, tiles, 0, 0)
 
     def prefetch_all(self, fused_buckets=()) -> None:
         """Queue the standalone all-gather (forward order) behind the updates for every bucket that

@@ -63,6 +63,7 @@ class Zero1Engine:
         bucket_of=default_bucket_of,
         ag_gemm: bool = True,
         comm_sms="auto",
+        clip_mode: str = "elementwise",
     ):
         self.model = model
         self.group = group
@@ -86,6 +87,13 @@ class Zero1Engine:
         self.beta1, self.beta2 = float(betas[0]), float(betas[1])
         self.eps = float(eps)
         self.clip = clip
+        # "elementwise": clamp every gradient element to [-clip, clip] (optax.clip, reference main_zero.py:161),
+        # single pass, fused into the update kernel.  "global_norm": scale by min(1, clip / ||g||_2) -- needs the
+        # norm of the fully reduced gradient first, so the fused backend runs reduce-scatter and AdamW as two phases.
+        if clip_mode not in ("elementwise", "global_norm"):
+            raise ValueError(f"unknown clip_mode '{clip_mode}'")
+        self.clip_mode = clip_mode
+        self.last_grad_norm: Optional[torch.Tensor] = None
         self.grad_accum_steps = int(grad_accum_steps)
         self.step_count = 0  # optimizer updates applied so far
 
@@ -173,7 +181,10 @@ class Zero1Engine:
             return
         b = self._block_bucket.get(i)
         if b is not None and b not in self._updated:
-            self._fused.bucket_update(b, side_sms=self.comm_sms, **self._adam_kwargs())
+            if self._two_phase:
+                self._fused.bucket_reduce(b)
+            else:
+                self._fused.bucket_update(b, side_sms=self.comm_sms, **self._adam_kwargs())
             self._updated.add(b)
 
     def _on_block_forward_pre(self, i: int) -> None:
@@ -254,9 +265,18 @@ class Zero1Engine:
             if not self._updated:
                 f.begin_step()          # no bucket was started from backward (plain loss.backward())
             kw = self._adam_kwargs()
-            for b in range(f.nb):       # whatever backward did not start: embed bucket, or everything
-                if b not in self._updated:
+            if self._two_phase:
+                for b in range(f.nb):
+                    if b not in self._updated:
+                        f.bucket_reduce(b)
+                coef = self._global_norm_coef(scale, stream=f.stream)
+                kw.update(clip=0.0, reduced=True, scale_mul=coef)
+                for b in range(f.nb):
                     f.bucket_update(b, **kw)
+            else:
+                for b in range(f.nb):       # whatever backward did not start: embed bucket, or everything
+                    if b not in self._updated:
+                        f.bucket_update(b, **kw)
             self._updated.clear()
             # all-gather: embed bucket (+ anything without a fused consumer) by the standalone P2P pull,
             # queued now so it overlaps the tail of this step; block buckets inside their QKV GEMM
@@ -267,16 +287,40 @@ class Zero1Engine:
                 f.wait_all()
         else:
             self._reduce_to_shard()
+            clip = self.clip
+            if self._two_phase:
+                scale = scale * float(self._global_norm_coef(scale, shard=self._grad_shard))
+                clip = None
             with torch.no_grad():
                 reference.adamw_step_(
                     self.master, self._grad_shard, self.exp_avg, self.exp_avg_sq,
                     lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps,
-                    wd=self.decay_vec * self.weight_decay, step=t, clip=self.clip, grad_scale=scale,
+                    wd=self.decay_vec * self.weight_decay, step=t, clip=clip, grad_scale=scale,
                 )
                 self.layout.scatter_shard_to_flat(self.master.to(self.compute_dtype), self.flat_param, self.rank)
             self._all_gather_params()
         self.step_count += 1
         return lr
+
+    @property
+    def _two_phase(self) -> bool:
+        return self.clip_mode == "global_norm" and bool(self.clip)
+
+    def _global_norm_coef(self, scale: float, shard: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
+        """min(1, clip / ||scale * g||_2) as a 1-element fp32 device tensor; ``g`` is the reduced gradient whose
+        shards live on the ranks (``shard``, or this rank's chunks of the flat buffer after ``bucket_reduce``)."""
+        import contextlib
+
+        ctx = torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+        with ctx, torch.no_grad():
+            if shard is None:
+                shard = self.layout.gather_shard_from_flat(self.flat_grad, self.rank)
+            sq = shard.float().pow(2).sum().reshape(1)
+            if self.world > 1:
+                dist.all_reduce(sq, op=dist.ReduceOp.SUM, group=self.group)
+            norm = sq.sqrt() * scale
+            self.last_grad_norm = norm
+            return torch.clamp(float(self.clip) / (norm + 1e-6), max=1.0)
 
     # -- unfused collectives --------------------------------------------
     def _reduce_to_shard(self) -> None:
@@ -413,7 +457,9 @@ class PlainAdamW:
     ``ndim >= 2`` decay mask).  The oracle for the ZeRO-1 equivalence tests and
     the optimizer of the single-process reference arm."""
 
-    def __init__(self, model, *, lr_fn, weight_decay=0.1, betas=(0.9, 0.95), eps=1e-8, clip=1.0, grad_accum_steps=1, world=1):
+    def __init__(self, model, *, lr_fn, weight_decay=0.1, betas=(0.9, 0.95), eps=1e-8, clip=1.0, grad_accum_steps=1, world=1,
+                 clip_mode="elementwise"):
+        self.clip_mode = clip_mode
         self.params = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
         self.lr_fn = lr_fn
         self.wd, self.b1, self.b2, self.eps, self.clip = weight_decay, betas[0], betas[1], eps, clip
@@ -431,11 +477,15 @@ class PlainAdamW:
         lr = float(self.lr_fn(self.step_count))
         t = self.step_count + 1
         with torch.no_grad():
+            scale, clip = self.scale, self.clip
+            if self.clip_mode == "global_norm" and clip:
+                norm = torch.sqrt(sum((p.grad.float() * scale).pow(2).sum() for _, p in self.params if p.grad is not None))
+                scale, clip = scale * min(1.0, float(clip) / (float(norm) + 1e-6)), None
             for n, p in self.params:
                 if p.grad is None:
                     continue
                 reference.adamw_step_(self.master[n], p.grad, self.m[n], self.v[n], lr=lr, beta1=self.b1, beta2=self.b2,
-                                      eps=self.eps, wd=self.wd if p.ndim >= 2 else 0.0, step=t, clip=self.clip, grad_scale=self.scale)
+                                      eps=self.eps, wd=self.wd if p.ndim >= 2 else 0.0, step=t, clip=clip, grad_scale=scale)
                 p.copy_(self.master[n].to(p.dtype))
         self.step_count += 1
         return lr

@@ -82,6 +82,7 @@ class Trainer:
             grad_dtype=(gd if on_gpu else torch.float32),
             ag_gemm=bool(t.get("ag_gemm", True)),
             comm_sms=t.get("comm_sms", "auto"),
+            clip_mode=str(t.get("grad_clip_mode", "elementwise")),
         )
         self.log.debug(self.engine.memory_report())
         self.log.debug("model %s: %.1fM parameters; optimizer state sharded over %d rank(s); params/grads/activations replicated",
