@@ -65,7 +65,7 @@ def main():
     fc.flat_grad.normal_()
     fc.flat_param.normal_()
     total_bytes = L.total * 2
-    out = {"world": n, "params": L.total, "bytes_bf16": total_bytes}
+    out = {"world": n, "params": L.total, "bytes_bf16": total_bytes, "nvls": bool(fc.nvls)}
     wire = total_bytes * (n - 1) / n  # bytes each rank must receive
 
     master = torch.randn(L.shard_total, device=dev)
@@ -81,12 +81,14 @@ def main():
     t = timed(fused_rs_adam)
     hbm = (2 * L.shard_total * n + 12 * L.shard_total + 14 * L.shard_total) / (pk["hbm_gbs"] * 1e9) * 1e3  # local part of the reads + state
     nv = wire / (NVLINK_GBS * 1e9) * 1e3
+    if fc.nvls:   # switch-side reduction: the shard comes in once; the push sends the shard out once, (n-1)/n of the model comes in
+        nv = max(2 * L.shard_total, wire) / (NVLINK_GBS * 1e9) * 1e3
     out["rs_adam_fused"] = {"ms": round(t, 3), "busbw_gbs": round(wire / t / 1e6, 1), "roofline_ms": round(max(hbm, nv), 3),
                             "roofline_frac": round(max(hbm, nv) / t, 3), "bound": "nvlink" if nv > hbm else "hbm"}
 
     if n > 1:
         def ag_pull():
-            fc.begin_step()
+            fc.begin_step()   # (_pushed reset: measures the P2P pull even when the NVLS push is available)
             with torch.cuda.stream(fc.stream):
                 for b in range(fc.nb):
                     fc._signal(FLAG_SHARD_READY, b, fc.epoch)

@@ -196,7 +196,7 @@ at::Tensor gemm_ag(const at::Tensor& A, const at::Tensor& B, std::vector<int64_t
 // peer's flat gradient buffer (first = local).  segs: uint8 CUDA tensor of packed ZtbSegment.
 void adamw_shard(at::Tensor& master, at::Tensor& m, at::Tensor& v, at::Tensor& flat_param, std::vector<int64_t> grad_ptrs,
                  bool grad_is_fp32, const at::Tensor& segs, int64_t nseg, int64_t total_tiles, double lr, double beta1, double beta2,
-                 double eps, double wd, double clip, double grad_scale, int64_t step, int64_t wait_flags_ptr, int64_t wait_value, int64_t side_sms, int64_t scale_mul_ptr) {
+                 double eps, double wd, double clip, double grad_scale, int64_t step, int64_t wait_flags_ptr, int64_t wait_value, int64_t side_sms, int64_t scale_mul_ptr, int64_t mc_grad_ptr, int64_t mc_param_ptr) {
   need(master.is_cuda() && master.scalar_type() == at::kFloat && m.scalar_type() == at::kFloat && v.scalar_type() == at::kFloat, "adamw_shard: fp32 state");
   need(is_bf16_cuda(flat_param), "adamw_shard: bf16 flat_param");
   need(segs.is_cuda() && segs.scalar_type() == at::kByte && segs.numel() >= (int64_t)(nseg * sizeof(ZtbSegment)), "adamw_shard: segs");
@@ -211,7 +211,8 @@ void adamw_shard(at::Tensor& master, at::Tensor& m, at::Tensor& v, at::Tensor& f
   a.bc2 = (float)(1.0 - std::pow(beta2, (double)step));
   check(ztb_adamw_shard(master.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), flat_param.data_ptr(), gp.data(), (int)gp.size(),
                         grad_is_fp32, reinterpret_cast<const ZtbSegment*>(segs.data_ptr()), (int)nseg, total_tiles, a,
-                        reinterpret_cast<const int*>(wait_flags_ptr), (int)wait_value, num_sms(), (int)side_sms, stream()), "adamw_shard");
+                        reinterpret_cast<const int*>(wait_flags_ptr), (int)wait_value, num_sms(), (int)side_sms, reinterpret_cast<const void*>(mc_grad_ptr),
+                        reinterpret_cast<void*>(mc_param_ptr), stream()), "adamw_shard");
 }
 
 int64_t segment_struct_size() { return sizeof(ZtbSegment); }
@@ -306,7 +307,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("adamw_shard", &adamw_shard, py::arg("master"), py::arg("m"), py::arg("v"), py::arg("flat_param"), py::arg("grad_ptrs"),
         py::arg("grad_is_fp32"), py::arg("segs"), py::arg("nseg"), py::arg("total_tiles"), py::arg("lr"), py::arg("beta1"), py::arg("beta2"),
         py::arg("eps"), py::arg("wd"), py::arg("clip"), py::arg("grad_scale"), py::arg("step"), py::arg("wait_flags_ptr") = 0,
-        py::arg("wait_value") = 0, py::arg("side_sms") = 0, py::arg("scale_mul_ptr") = 0);
+        py::arg("wait_value") = 0, py::arg("side_sms") = 0, py::arg("scale_mul_ptr") = 0, py::arg("mc_grad_ptr") = 0, py::arg("mc_param_ptr") = 0);
   m.def("set_sm_reserve", [](int64_t n) { g_sm_reserve = n < 0 ? 0 : (int)n; }, "persistent GEMMs leave this many SMs free");
   m.def("get_sm_reserve", []() { return (int64_t)g_sm_reserve; });
   m.def("segment_struct_size", &segment_struct_size);

@@ -38,7 +38,8 @@ struct ZtbAdamArgs {
 // grads[p] = flat grad buffer of peer p (p = 0 is local); n_peers == 1 -> plain fused AdamW.
 int ztb_adamw_shard(float* master, float* m, float* v, void* flat_param, const void* const* grads, int n_peers,
                     int grad_is_fp32, const ZtbSegment* segs, int nseg, long long total_tiles, ZtbAdamArgs a,
-                    const int* wait_flags, int wait_value, int sms, int side_sms, cudaStream_t st);
+                    const int* wait_flags, int wait_value, int sms, int side_sms, const void* mc_grad, void* mc_param,
+                    cudaStream_t st);
 
 // ---- gemm_tcgen05.cu
 enum ZtbEpilogue { ZTB_EPI_NONE = 0, ZTB_EPI_GELU = 1, ZTB_EPI_DROPOUT_ADD = 2, ZTB_EPI_GELU_BWD = 3 };

@@ -26,6 +26,19 @@ struct PeerPtrs {
   const void* g[kMaxPeers];
 };
 
+// NVLS: one instruction returns the sum over every rank's copy of 8 bf16 values (the NVSwitch reduces; fp32
+// accumulation, bf16 result); the store is replicated by the switch into every rank's buffer.
+ZTB_DEVINL uint4 multimem_ld_reduce_bf16x8(const bf16* mc) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(mc) : "memory");
+  return r;
+}
+ZTB_DEVINL void multimem_st_bf16x8(bf16* mc, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1, %2, %3, %4};"
+               ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 ZTB_DEVINL uint32_t ld_acquire_sys(const int* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -42,7 +55,8 @@ __global__ void __launch_bounds__(kThreads) adamw_shard_kernel(float* __restrict
                                                                    PeerPtrs peers, int n_peers,
                                                                    const ZtbSegment* __restrict__ segs, int nseg,
                                                                    long long total_tiles, ZtbAdamArgs a,
-                                                                   const int* __restrict__ wait_flags, int wait_value) {
+                                                                   const int* __restrict__ wait_flags, int wait_value,
+                                                                   const bf16* __restrict__ mc_grad, bf16* __restrict__ mc_param) {
   if (wait_flags != nullptr) {
     // every peer publishes "my gradients for this bucket are final" with a release store into OUR
     // signal pad; acquire it before touching peer memory.
@@ -68,6 +82,11 @@ __global__ void __launch_bounds__(kThreads) adamw_shard_kernel(float* __restrict
     float g[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) g[k] = 0.f;
+    if (!kGradFp32 && mc_grad != nullptr) {
+      uint4 u = multimem_ld_reduce_bf16x8(mc_grad + fo);
+      float2 x0 = unpack_bf16(u.x), x1 = unpack_bf16(u.y), x2 = unpack_bf16(u.z), x3 = unpack_bf16(u.w);
+      g[0] = x0.x; g[1] = x0.y; g[2] = x1.x; g[3] = x1.y; g[4] = x2.x; g[5] = x2.y; g[6] = x3.x; g[7] = x3.y;
+    } else
     for (int p = 0; p < n_peers; ++p) {
       if constexpr (kGradFp32) {
         const float4* gp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(peers.g[p]) + fo);
@@ -100,7 +119,8 @@ __global__ void __launch_bounds__(kThreads) adamw_shard_kernel(float* __restrict
     }
     pm[0] = P[0]; pm[1] = P[1]; mm[0] = Mo[0]; mm[1] = Mo[1]; vv[0] = Vo[0]; vv[1] = Vo[1];
     uint4 o = make_uint4(pack_bf16(pf[0], pf[1]), pack_bf16(pf[2], pf[3]), pack_bf16(pf[4], pf[5]), pack_bf16(pf[6], pf[7]));
-    st_v4(flat_param + fo, o);
+    if (mc_param != nullptr) multimem_st_bf16x8(mc_param + fo, o);   // the all-gather: pushed to every rank by the switch
+    else st_v4(flat_param + fo, o);
   }
 }
 
@@ -113,8 +133,8 @@ constexpr int kSideSmem = 120 * 1024;   // more than half an SM's shared memory:
 
 template <bool kGradFp32>
 static int launch_side(float* master, float* m, float* v, bf16* flat_param, const PeerPtrs& pp, int n_peers, const ZtbSegment* segs,
-                       int nseg, long long total_tiles, const ZtbAdamArgs& a, const int* wait_flags, int wait_value, int ctas,
-                       cudaStream_t st) {
+                       int nseg, long long total_tiles, const ZtbAdamArgs& a, const int* wait_flags, int wait_value, const bf16* mc_grad, bf16* mc_param,
+                       int ctas, cudaStream_t st) {
   auto kern = adamw_shard_kernel<kGradFp32, kSideThreads>;
   static bool configured = false;
   if (!configured) {
@@ -130,7 +150,7 @@ static int launch_side(float* master, float* m, float* v, bf16* flat_param, cons
   attr[0].id = cudaLaunchAttributeClusterDimension;   // a pair lands on one TPC: the same granularity the 2-CTA GEMM needs
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  ZTB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, master, m, v, flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value));
+  ZTB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, master, m, v, flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value, mc_grad, mc_param));
   return 0;
 }
 
@@ -138,22 +158,26 @@ static int launch_side(float* master, float* m, float* v, bf16* flat_param, cons
 // persistent kernels instead of spreading over the whole GPU.
 int ztb_adamw_shard(float* master, float* m, float* v, void* flat_param, const void* const* grads, int n_peers,
                     int grad_is_fp32, const ZtbSegment* segs, int nseg, long long total_tiles, ZtbAdamArgs a,
-                    const int* wait_flags, int wait_value, int sms, int side_sms, cudaStream_t st) {
+                    const int* wait_flags, int wait_value, int sms, int side_sms, const void* mc_grad_, void* mc_param_,
+                    cudaStream_t st) {
+  const bf16* mc_grad = (const bf16*)mc_grad_;
+  bf16* mc_param = (bf16*)mc_param_;
+  if (grad_is_fp32 && mc_grad != nullptr) { ztb_set_error("adamw_shard", "multicast reduce needs bf16 gradients", __FILE__, __LINE__); return -1; }
   if (n_peers < 1 || n_peers > kMaxPeers) { ztb_set_error("adamw_shard", "n_peers out of range", __FILE__, __LINE__); return -1; }
   if (total_tiles <= 0) return 0;
   PeerPtrs pp;
   for (int i = 0; i < kMaxPeers; ++i) pp.g[i] = i < n_peers ? grads[i] : nullptr;
   if (side_sms > 0) {
     int ctas = side_sms < 2 ? 2 : (side_sms & ~1);
-    return grad_is_fp32 ? launch_side<true>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value, ctas, st)
-                        : launch_side<false>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value, ctas, st);
+    return grad_is_fp32 ? launch_side<true>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value, mc_grad, mc_param, ctas, st)
+                        : launch_side<false>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value, mc_grad, mc_param, ctas, st);
   }
   long long want = total_tiles < (long long)sms * 16 ? total_tiles : (long long)sms * 16;
   int grid = (int)want;
   if (grad_is_fp32)
-    adamw_shard_kernel<true, kAdamThreads><<<grid, kAdamThreads, 0, st>>>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value);
+    adamw_shard_kernel<true, kAdamThreads><<<grid, kAdamThreads, 0, st>>>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value, mc_grad, mc_param);
   else
-    adamw_shard_kernel<false, kAdamThreads><<<grid, kAdamThreads, 0, st>>>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value);
+    adamw_shard_kernel<false, kAdamThreads><<<grid, kAdamThreads, 0, st>>>(master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value, mc_grad, mc_param);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

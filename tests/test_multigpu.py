@@ -21,7 +21,8 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, backend, out, clip_mode="elementwise", clip=1.0):
+def _worker(rank, world, port, backend, out, clip_mode="elementwise", clip=1.0, nvls="1"):
+    os.environ["ZTB_NVLS"] = nvls
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -55,7 +56,8 @@ def _worker(rank, world, port, backend, out, clip_mode="elementwise", clip=1.0):
         same = bool(torch.equal(flat, ref))
         st = eng.consolidated_state(0)
         if rank == 0:
-            torch.save({"params": st["params"], "init": init["params"], "losses": losses, "same": same}, out)
+            torch.save({"params": st["params"], "init": init["params"], "losses": losses, "same": same,
+                        "nvls": bool(getattr(eng._fused, "nvls", False))}, out)
         ok = torch.tensor([int(same)], device="cuda")
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         assert ok.item() == 1, "ranks disagree on gathered parameters"
@@ -63,16 +65,21 @@ def _worker(rank, world, port, backend, out, clip_mode="elementwise", clip=1.0):
         dist.destroy_process_group()
 
 
-def _run(backend, tmp_path, world=2, clip_mode="elementwise", clip=1.0):
-    out = str(tmp_path / f"{backend}_{clip_mode}.pt")
-    mp.spawn(_worker, args=(world, _free_port(), backend, out, clip_mode, clip), nprocs=world, join=True)
+def _run(backend, tmp_path, world=2, clip_mode="elementwise", clip=1.0, nvls="1"):
+    out = str(tmp_path / f"{backend}_{clip_mode}_{nvls}.pt")
+    mp.spawn(_worker, args=(world, _free_port(), backend, out, clip_mode, clip, nvls), nprocs=world, join=True)
     return torch.load(out, weights_only=False)
 
 
-def test_fused_backend_matches_nccl_backend(tmp_path):
-    a = _run("fused", tmp_path)
+@pytest.mark.parametrize("nvls", ["1", "0"])
+def test_fused_backend_matches_nccl_backend(tmp_path, nvls):
+    """nvls=1: switch-side reduction + multicast push when the symmetric buffers have a multicast mapping
+    (falls back to the P2P kernels otherwise); nvls=0: P2P loads + all-gather fused into the QKV GEMM."""
+    a = _run("fused", tmp_path, nvls=nvls)
     b = _run("nccl", tmp_path)
     assert a["same"] and b["same"]
+    assert nvls == "1" or not a["nvls"]
+    print("nvls active:", a["nvls"])
     assert a["losses"] == pytest.approx(b["losses"], rel=2e-2)
     # Adam normalises the update, so bf16-level differences in the reduced gradient (NCCL sums in
     # bf16, the fused kernel in fp32) move individual elements by O(lr); compare the update vectors.

@@ -18,6 +18,7 @@ single "peer" and ordinary allocations.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -128,6 +129,13 @@ class FusedComm:
         self.ready = [torch.cuda.Event() for _ in range(self.nb)]       # bucket b usable by compute
         self._ev = torch.cuda.Event()
         self._pending = [False] * self.nb
+        # NVLS: with a multicast mapping of both flat buffers the update kernel reduces the gradients in the
+        # switch (multimem.ld_reduce) and pushes the new bf16 chunk to every rank (multimem.st): reduce-scatter,
+        # AdamW and all-gather are one kernel, and the consumer only waits for the SHARD_READY flags.
+        self.nvls = bool(world > 1 and os.environ.get("ZTB_NVLS", "1") != "0" and not self.grad_fp32
+                         and getattr(self._grad, "multicast_ptr", 0) and getattr(self._param, "multicast_ptr", 0))
+        self._pushed = [False] * self.nb      # bucket's new chunk was multicast to every rank by its owner
+        self._flagwait = [False] * self.nb    # ... so the consumer waits for the owners' flags instead of pulling
         if world > 1:
             dist.barrier(group)
 
@@ -148,6 +156,7 @@ class FusedComm:
     # per-step protocol --------------------------------------------------
     def begin_step(self) -> None:
         self.epoch += 1
+        self._pushed = [False] * self.nb
 
     def bucket_update(self, b: int, *, master, m, v, lr, beta1, beta2, eps, wd, step, clip, grad_scale, side_sms: int = 0,
                       reduced: bool = False, scale_mul: Optional[torch.Tensor] = None) -> None:
@@ -164,8 +173,11 @@ class FusedComm:
             segs, n, tiles = self.adam[b]
             # reduced=True: bucket_reduce() already left the cross-rank sum in the local buffer
             ptrs = self._grad.ptrs[self.rank:self.rank + 1] if (reduced or self.world == 1) else self.grad_ptrs
+            mc_grad = self._grad.multicast_ptr if (self.nvls and not reduced) else 0
+            mc_param = self._param.multicast_ptr if self.nvls else 0
             self._C.adamw_shard(master, m, v, self.flat_param, ptrs, self.grad_fp32, segs, n, tiles, lr, beta1, beta2, eps, wd, clip,
-                                grad_scale, step, 0, 0, side_sms, scale_mul.data_ptr() if scale_mul is not None else 0)
+                                grad_scale, step, 0, 0, side_sms, scale_mul.data_ptr() if scale_mul is not None else 0, mc_grad, mc_param)
+            self._pushed[b] = bool(mc_param)
             if self.world > 1:
                 self._signal(FLAG_SHARD_READY, b, e)
             else:
@@ -193,11 +205,14 @@ class FusedComm:
         if self.world == 1:
             return
         e = self.epoch
-        for b in fused_buckets:
-            self._ag_pending[b] = True
+        for b in range(self.nb):
+            if self._pushed[b]:
+                self._flagwait[b] = True       # nothing to pull: every owner multicast its chunk
+            elif b in fused_buckets:
+                self._ag_pending[b] = True
         with torch.cuda.stream(self.stream):
             for b in range(self.nb):
-                if b in fused_buckets:
+                if b in fused_buckets or self._pushed[b]:
                     continue
                 self._C.wait_flags(self._my_row(FLAG_SHARD_READY, b), self.world, e)
                 segs, n, tiles = self.pull[b]
@@ -244,6 +259,11 @@ class FusedComm:
             self._C.wait_flags(self._my_row(FLAG_SHARD_READY, b), self.world, self.epoch)
             segs, n, tiles = self.pull[b]
             self._C.allgather_pull(self.flat_param, self._param.ptrs, segs, n, tiles, 0, 0)
+            self._pending[b] = False
+            return
+        if self._flagwait[b]:
+            self._flagwait[b] = False
+            self._C.wait_flags(self._my_row(FLAG_SHARD_READY, b), self.world, self.epoch)   # one warp, compute stream
             self._pending[b] = False
             return
         if self._pending[b]:
