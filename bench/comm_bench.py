@@ -23,7 +23,7 @@ import torch.distributed as dist
 from zero_transformer_b200.models.gpt import GPTConfig
 from zero_transformer_b200.ops import cuda as K
 from zero_transformer_b200.parallel import dist as pdist
-from zero_transformer_b200.parallel.fused import FLAG_GRAD_READY, FLAG_SHARD_READY, FusedComm, pack_segments
+from zero_transformer_b200.parallel.fused import FLAG_SHARD_READY, FusedComm, pack_segments
 from zero_transformer_b200.parallel.layout import FlatLayout
 from zero_transformer_b200.utils.metrics import measured_peaks
 

@@ -12,8 +12,8 @@ import torch
 import yaml
 
 from zero_transformer_b200.models.gpt import GPTConfig, Transformer
-from zero_transformer_b200.utils.export import (from_flax_params, from_reference_state_dict, load_flax_msgpack,
-                                                save_reference_pth, to_reference_state_dict)
+from zero_transformer_b200.utils.export import (from_reference_state_dict, load_flax_msgpack, save_reference_pth,
+                                                to_reference_state_dict)
 
 REF = "/root/reference/torch_compatability/GPT2.py"
 

@@ -173,8 +173,6 @@ def test_cross_entropy_fwd_bwd(K, V):
 
 
 def test_fused_adamw_matches_reference(K):
-    import numpy as np
-
     from zero_transformer_b200.ops.reference import adamw_step_
     from zero_transformer_b200.parallel.fused import pack_segments
 

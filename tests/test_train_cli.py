@@ -1,6 +1,5 @@
 """End-to-end driver on CPU: train -> checkpoint -> resume -> export -> generate."""
 import json
-import os
 
 import torch
 

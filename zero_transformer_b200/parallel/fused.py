@@ -19,7 +19,7 @@ single "peer" and ordinary allocations.
 from __future__ import annotations
 
 import os
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -295,8 +295,6 @@ class FusedComm:
 
 def p2p_probe(env) -> Dict[str, object]:
     """Peer reachability + NVLink bandwidth estimate for ``utils.selftest`` (pod_test analogue)."""
-    import time
-
     from ..ops._build import load
 
     C = load()

@@ -28,7 +28,6 @@ tensors on the hot path.
 """
 from __future__ import annotations
 import os
-import math
 from typing import Callable, Dict, Optional
 
 import torch

@@ -15,13 +15,11 @@ from __future__ import annotations
 import argparse
 import math
 import os
-import time
 from typing import Dict, Iterable, Iterator, Optional
 
 import numpy as np
 import torch
 
-from . import ops
 from .config import DEFAULT_CFG, DEFAULT_MODEL_CFG, Config, flatten_dict, load_config
 from .data.pipeline import (DevicePrefetcher, StreamingTokenDataset, SyntheticTokenDataset, batch_iterator, rechunk,
                             to_micro_batches)
