@@ -153,7 +153,8 @@ class TransformerBlock(nn.Module):
 class Transformer(nn.Module):
     """Full model.  ``model(x)`` -> logits ``(B, T, V)``; ``model(x, labels)`` ->
     ``(logits, loss)`` like reference ``GPT.py:68-113``; ``model.loss(x)`` is the
-    training entry that never materialises the logits (fused LM head + CE)."""
+    training entry: LM-head GEMM + cross entropy as one autograd node that keeps a single bf16
+    logits buffer (no fp32 logits, no softmax tensor) and turns it into the gradient in place."""
 
     def __init__(self, cfg: GPTConfig):
         super().__init__()
