@@ -1,4 +1,7 @@
 // NVLink / NVSwitch communication kernels over symmetric (peer-mapped) memory.  No NCCL.
+// They replace the reference's collectives: the gradient pmean of src/training/xmap_train_functions.py:84
+// (a reduce-scatter is all ZeRO-1 needs) and the parameter all-gather XLA inserts for
+// main_zero.py:452-456; src/utils/pod_test.py:17-34 is the health probe ztb_p2p_copy serves.
 //
 //   ztb_signal            release-store a step counter into every peer's flag pad
 //   ztb_allgather_pull    every rank pulls the other ranks' freshly updated bf16 parameter chunks

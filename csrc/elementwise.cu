@@ -1,7 +1,9 @@
 // Memory-bound sm_100a kernels: LayerNorm (bias-free) fwd/bwd, dropout+residual fwd/bwd,
 // embedding gather / scatter-add, GELU backward, cross-entropy fwd/bwd over bf16 logits.
 // All are single-pass over HBM with 16-byte vector accesses; row reductions stay in
-// registers + warp shuffles.  Reference semantics: SURVEY 2.4-A rows K2, K3, K9, K11.
+// registers + warp shuffles.  Reference semantics: SURVEY 2.4-A rows K2, K3, K9, K11 -- embedding gather
+// src/models/GPT.py:75-83, bias-free LayerNorm GPT.py:42,49,98, dropout + residual layers.py:77,191 and
+// GPT.py:43-49, tanh-GELU layers.py:68, shifted cross entropy GPT.py:105-111 + src/utils/losses.py:9-23.
 #include "common.cuh"
 #include "launchers.h"
 

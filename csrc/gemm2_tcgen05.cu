@@ -1,10 +1,12 @@
 // 2-CTA (cta_group::2) variant of the tcgen05 GEMM: a pair of CTAs on one TPC computes a 256x256
 // tile.  Each CTA stages 128 rows of A and 128 rows (N) of B per 64-wide K block -- 32 KB instead of
 // the 48 KB a lone 128x256 CTA needs for the same MMA work -- so the L2 -> SM traffic per FLOP drops
-// by a third and the smem ring deepens to 6 stages.  The leader CTA issues
+// by a third and the smem ring deepens to 5 stages (the rest of the 227 KB is the 64 KB epilogue staging).  The leader CTA issues
 // tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' smem and writes both CTAs' TMEM;
 // completion is multicast to both CTAs' mbarriers.  Everything else (operand majors, epilogues,
 // TMEM double buffering, TMA store / reduce-add) matches gemm_tcgen05.cu.
+// Reference call sites served: the q/k/v, attention-output and MLP projections and their autodiff transposes
+// (src/models/layers.py:60-77,112-143,180-189), which XLA lowered to MXU dots.
 #include <cuda.h>
 #include <stdio.h>
 

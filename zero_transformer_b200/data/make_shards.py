@@ -1,5 +1,6 @@
 """Build token shards + an index file for ``StreamingTokenDataset`` (the reference consumes
-pre-tokenised WebDataset tars listed in ``data/index/*.index``; this is the local equivalent).
+pre-tokenised WebDataset tars listed in ``data/index/*.index``, ``main_zero.py:368-421``, each sample an
+``input_id.pth`` of ``max_context`` tokens; this is the local equivalent).
 
     python -m zero_transformer_b200.data.make_shards --tokens corpus.npy --out data/shards \
         --max-context 2048 --samples-per-shard 4096 --index data/index/train.index

@@ -1,4 +1,8 @@
-"""Autograd wrapper of the tcgen05 ALiBi flash-attention kernels (csrc/attention.cu)."""
+"""Autograd wrapper of the tcgen05 ALiBi flash-attention kernels (csrc/attention.cu).
+
+Same math as the reference's ``CausalAttention`` core (``src/models/layers.py:145-178``: scaled scores + ALiBi
+bias ``slope_h * (j - i)`` from ``get_slopes``/``create_mask`` ``layers.py:17-44``, causal mask, fp32 softmax,
+dropout on the probabilities, ``P V``) without materialising the ``(b, nh, T, T)`` score tensor."""
 from __future__ import annotations
 
 import torch

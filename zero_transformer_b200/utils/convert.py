@@ -1,7 +1,7 @@
 """Checkpoint conversion CLI.
 
-Covers the reference's two converter scripts: ``torch_compatability/extract_msgpack.py``
-(training checkpoint -> bare parameter file) and ``torch_compatability/convert_to_torch.py``
+Covers the reference's two converter scripts: ``torch_compatability/extract_msgpack.py:28-62``
+(training checkpoint -> bare parameter file) and ``torch_compatability/convert_to_torch.py:26-31``
 (``--model-name --flax-path --torch-path [--vocab-size --seq-len]`` -> ``.pth``).
 
     python -m zero_transformer_b200.utils.convert extract --ckpt-dir checkpoints --step 1000 --out params.pt
