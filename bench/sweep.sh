@@ -17,7 +17,7 @@ ARM=
 run ZTB_BENCH_MODEL=417m
 run ZTB_BENCH_MODEL=760m
 run ZTB_BENCH_MODEL=1_3b
-run ZTB_BENCH_MODEL=1_3b ZTB_BENCH_SEQ=2048 ZTB_BENCH_ROWS=16 ZTB_BENCH_ACCUM=8     # BASELINE config #5 shape: 32k tokens per GPU per step
+run ZTB_BENCH_MODEL=1_3b ZTB_BENCH_SEQ=2048 ZTB_BENCH_ROWS=64 ZTB_BENCH_ACCUM=8     # BASELINE config #5 shape: 8 micro-batches of 8 x 2048 tokens per GPU per step
 run ZTB_BENCH_MODEL=1_3b ZTB_NVLS=0                                                 # P2P data plane
 ARM=baseline
 run ZTB_BENCH_MODEL=1_3b                                                            # stock PyTorch + NCCL arm
