@@ -194,8 +194,6 @@ class Zero1Engine:
     def _install_ag_gemm(self, model) -> None:
         """Tag every block's QKV weight -- the first GEMM that consumes the block's bucket -- so that
         ``ops.linear`` runs the all-gather-fused GEMM when that bucket still has to be gathered."""
-        import os
-
         if self.world == 1 or not self.ag_gemm or os.environ.get("ZTB_AG_GEMM", "1") != "1":
             return
         fused = []
