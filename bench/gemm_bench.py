@@ -72,6 +72,25 @@ def main():
         r["dgrad_gelu_bwd"] = round(fl / timeit(lambda: K._C.gemm(dy, w2, epilogue=K.EPI_GELU_BWD, aux_in=z, b_mn=True, two_cta=two)) / 1e9, 1)
         r["dgrad_plain"] = round(fl / timeit(lambda: K._C.gemm(dy, w2, b_mn=True, two_cta=two)) / 1e9, 1)
         print(json.dumps(r), flush=True)
+    # ---- round 2: staging-free (direct st.global) outputs and the vocabulary raster
+    for direct in (0, 1, 2, 3):
+        r = {"direct_store": direct}
+        r["fc_in_gelu"] = round(fl / timeit(lambda: K._C.gemm(x, w1, epilogue=K.EPI_GELU, aux_out=z, two_cta=True, direct_store=direct)) / 1e9, 1)
+        r["fc_out_dropout_add"] = round(fl / timeit(lambda: K._C.gemm(z, w2, epilogue=K.EPI_DROPOUT_ADD, aux_in=res, p=0.1, rng=rng, op_id=1, two_cta=True, direct_store=direct)) / 1e9, 1)
+        r["dgrad_gelu_bwd"] = round(fl / timeit(lambda: K._C.gemm(dy, w2, epilogue=K.EPI_GELU_BWD, aux_in=z, b_mn=True, two_cta=True, direct_store=direct)) / 1e9, 1)
+        r["fc_in_plain"] = round(fl / timeit(lambda: K._C.gemm(x, w1, two_cta=True, direct_store=direct)) / 1e9, 1)
+        print(json.dumps(r), flush=True)
+    V = 50304
+    h = torch.randn(m, d, device="cuda").bfloat16()
+    wte = torch.randn(V, d, device="cuda").bfloat16() * 0.02
+    dl = torch.randn(m, V, device="cuda").bfloat16()
+    flv = 2.0 * m * V * d
+    for label, kw in (("1cta", dict(two_cta=False)), ("2cta_raster_m", dict(two_cta=True, raster_n=0)), ("2cta_raster_n", dict(two_cta=True, raster_n=1))):
+        r = {"lm_head": label}
+        r["fwd"] = round(flv / timeit(lambda: K._C.gemm(h, wte, **kw)) / 1e9, 1)
+        r["dgrad"] = round(flv / timeit(lambda: K._C.gemm(dl, wte, b_mn=True, **kw)) / 1e9, 1)
+        r["wgrad"] = round(flv / timeit(lambda: K._C.gemm(dl, h, a_mn=True, b_mn=True, **kw)) / 1e9, 1)
+        print(json.dumps(r), flush=True)
     return rows
 
 

@@ -1,0 +1,14 @@
+#!/bin/bash
+# Round-2 call 1 (1 GPU): kernel numerics, GEMM variants, A/B of the background optimizer update, step profile.
+mkdir -p gpurun_out
+set -x
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_model_gpu.py -x -q -m gpu > gpurun_out/r2_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2_tests.log
+tail -n 5 gpurun_out/r2_tests.log
+timeout 600 python bench/gemm_bench.py > gpurun_out/r2_gemm_bench.jsonl 2> gpurun_out/r2_gemm_bench.err
+tail -n 9 gpurun_out/r2_gemm_bench.jsonl
+ZTB_UPDATE_MODE=wide timeout 600 python bench.py --steps 6 --warmup 3 2>gpurun_out/r2_bench_wide.err | tail -1 > gpurun_out/r2_bench_wide.json
+cat gpurun_out/r2_bench_wide.json
+timeout 600 python bench.py --steps 6 --warmup 3 2>gpurun_out/r2_bench_bg.err | tail -1 > gpurun_out/r2_bench_bg.json
+cat gpurun_out/r2_bench_bg.json
+timeout 600 python bench/gap_analysis.py > gpurun_out/r2_gap.txt 2>&1
+tail -n 34 gpurun_out/r2_gap.txt

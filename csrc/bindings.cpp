@@ -19,12 +19,6 @@ int num_sms() {
   if (!n) n = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   return n;
 }
-// SMs that persistent GEMMs leave free for a concurrently running side kernel (fused reduce-scatter + AdamW)
-int g_sm_reserve = 0;
-int gemm_sms() {
-  int n = num_sms() - g_sm_reserve;
-  return n < 2 ? 2 : n;
-}
 void need(bool c, const char* msg) {
   if (!c) throw std::invalid_argument(msg);
 }
@@ -43,19 +37,48 @@ std::vector<at::Tensor> layernorm_fwd(const at::Tensor& x, const at::Tensor& w, 
   return {y, mean, rstd};
 }
 
+// Returns {dx, dw, dmask}.  With `grad_out` (the weight's gradient buffer, bf16 or fp32) the kernel's last block writes /
+// accumulates the weight gradient there and dw is an empty tensor; `scratch` (fp32 [D]) and `ticket` (int32 [1]) are
+// persistent, zero on entry and zero again on exit.  drop_p > 0: also return dmask = dropout_mask(dx) / (1 - p).
 std::vector<at::Tensor> layernorm_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& w, const at::Tensor& mean,
-                                      const at::Tensor& rstd, const c10::optional<at::Tensor>& dres) {
+                                      const at::Tensor& rstd, const c10::optional<at::Tensor>& dres,
+                                      const c10::optional<at::Tensor>& grad_out, bool accumulate,
+                                      const c10::optional<at::Tensor>& scratch, const c10::optional<at::Tensor>& ticket,
+                                      double drop_p, const c10::optional<at::Tensor>& rng, int64_t op_id) {
   need(is_bf16_cuda(dy) && is_bf16_cuda(x) && dy.is_contiguous() && x.is_contiguous(), "layernorm_bwd: bf16 contiguous");
   c10::cuda::CUDAGuard g(x.device());
   int D = x.size(-1);
   int M = x.numel() / D;
   auto dx = at::empty_like(x);
-  auto dw = at::empty({D}, x.options().dtype(at::kFloat));
   const void* dr = nullptr;
   if (dres.has_value()) { need(is_bf16_cuda(*dres) && dres->is_contiguous() && dres->numel() == x.numel(), "layernorm_bwd: bad dres"); dr = dres->data_ptr(); }
+  ZtbLnBwdExtra ex{};
+  at::Tensor dw, dmask;
+  float* dwp = nullptr;
+  if (grad_out.has_value()) {
+    need(scratch.has_value() && ticket.has_value(), "layernorm_bwd: grad_out needs scratch + ticket");
+    need(grad_out->is_cuda() && grad_out->is_contiguous() && grad_out->numel() == D &&
+         (grad_out->scalar_type() == at::kBFloat16 || grad_out->scalar_type() == at::kFloat), "layernorm_bwd: grad_out must be a contiguous bf16/fp32 [D] CUDA tensor");
+    need(scratch->is_cuda() && scratch->scalar_type() == at::kFloat && scratch->numel() >= D && scratch->is_contiguous(), "layernorm_bwd: scratch fp32 [D]");
+    need(ticket->is_cuda() && ticket->element_size() == 4 && ticket->numel() >= 1, "layernorm_bwd: ticket int32 [1]");
+    ex.grad_out = grad_out->data_ptr(); ex.grad_fp32 = grad_out->scalar_type() == at::kFloat; ex.grad_accumulate = accumulate;
+    ex.ticket = reinterpret_cast<unsigned int*>(ticket->data_ptr());
+    dwp = scratch->data_ptr<float>();
+    dw = at::empty({0}, x.options().dtype(at::kFloat));
+  } else {
+    dw = at::empty({D}, x.options().dtype(at::kFloat));
+    dwp = dw.data_ptr<float>();
+  }
+  if (drop_p > 0.0) {
+    need(rng.has_value() && rng->is_cuda() && rng->scalar_type() == at::kLong && rng->numel() >= 2, "layernorm_bwd: dropout output needs rng (CUDA int64[2])");
+    dmask = at::empty_like(x);
+    ex.dmask = dmask.data_ptr(); ex.p = (float)drop_p; ex.rng = (const uint64_t*)rng->data_ptr<int64_t>(); ex.op_id = (uint32_t)op_id;
+  } else {
+    dmask = at::empty({0}, x.options());
+  }
   check(ztb_layernorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(), dx.data_ptr(),
-                          dw.data_ptr<float>(), M, D, num_sms(), stream(), dr), "layernorm_bwd");
-  return {dx, dw};
+                          dwp, M, D, num_sms(), stream(), dr, &ex), "layernorm_bwd");
+  return {dx, dw, dmask};
 }
 
 at::Tensor dropout_add(const at::Tensor& y, const c10::optional<at::Tensor>& res, double p, const at::Tensor& rng, int64_t op_id) {
@@ -126,7 +149,8 @@ void ce_bwd_(at::Tensor& logits, const at::Tensor& labels, const at::Tensor& lse
 // C[M,N] (+)= op(A) * op(B)^T ; see launchers.h ZtbGemmArgs.  a_mn: A given as [K,M]; b_mn: B given as [K,N].
 at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tensor> C_, int64_t epilogue,
                 const c10::optional<at::Tensor>& aux_in, c10::optional<at::Tensor> aux_out, double p,
-                const c10::optional<at::Tensor>& rng, int64_t op_id, bool accumulate, bool a_mn, bool b_mn, bool two_cta, bool no_split) {
+                const c10::optional<at::Tensor>& rng, int64_t op_id, bool accumulate, bool a_mn, bool b_mn, bool two_cta, bool no_split,
+                int64_t direct_store, int64_t raster_n) {
   need(is_bf16_cuda(A) && is_bf16_cuda(B) && A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "gemm: A, B must be 2-D bf16 CUDA with unit inner stride");
   c10::cuda::CUDAGuard g(A.device());
   ZtbGemmArgs a{};
@@ -148,6 +172,7 @@ at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tens
   a.epilogue = (int)epilogue;
   a.accumulate = accumulate; a.c_is_fp32 = C.scalar_type() == at::kFloat;
   a.a_mn_major = a_mn; a.b_mn_major = b_mn; a.two_cta = two_cta; a.no_split = no_split;
+  a.direct_store = (int)direct_store; a.raster_n = (int)raster_n;
   a.p = (float)p; a.op_id = (uint32_t)op_id;
   if (aux_in.has_value()) {
     need(is_bf16_cuda(*aux_in) && aux_in->dim() == 2 && aux_in->size(0) == a.M && aux_in->size(1) == a.N && aux_in->stride(1) == 1, "gemm: bad aux_in");
@@ -162,7 +187,7 @@ at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tens
     a.rng = (const uint64_t*)rng->data_ptr<int64_t>();
   }
   need(epilogue != ZTB_EPI_DROPOUT_ADD || a.rng != nullptr, "gemm: dropout epilogue needs rng");
-  check(ztb_gemm(&a, gemm_sms(), stream()), "gemm");
+  check(ztb_gemm(&a, num_sms(), stream()), "gemm");
   return C;
 }
 
@@ -188,7 +213,8 @@ at::Tensor gemm_ag(const at::Tensor& A, const at::Tensor& B, std::vector<int64_t
   a.M = A.size(0); a.K = A.size(1); a.N = B.size(0);
   a.lda = A.stride(0); a.ldb = B.stride(0); a.ldc = C.stride(0);
   a.ag = &ag;
-  check(ztb_gemm(&a, gemm_sms(), stream()), "gemm_ag");
+  a.direct_store = -1; a.raster_n = -1;
+  check(ztb_gemm(&a, num_sms(), stream()), "gemm_ag");
   return C;
 }
 
@@ -196,7 +222,7 @@ at::Tensor gemm_ag(const at::Tensor& A, const at::Tensor& B, std::vector<int64_t
 // peer's flat gradient buffer (first = local).  segs: uint8 CUDA tensor of packed ZtbSegment.
 void adamw_shard(at::Tensor& master, at::Tensor& m, at::Tensor& v, at::Tensor& flat_param, std::vector<int64_t> grad_ptrs,
                  bool grad_is_fp32, const at::Tensor& segs, int64_t nseg, int64_t total_tiles, double lr, double beta1, double beta2,
-                 double eps, double wd, double clip, double grad_scale, int64_t step, int64_t wait_flags_ptr, int64_t wait_value, int64_t side_sms, int64_t scale_mul_ptr, int64_t mc_grad_ptr, int64_t mc_param_ptr) {
+                 double eps, double wd, double clip, double grad_scale, int64_t step, int64_t wait_flags_ptr, int64_t wait_value, int64_t max_ctas, int64_t scale_mul_ptr, int64_t mc_grad_ptr, int64_t mc_param_ptr) {
   need(master.is_cuda() && master.scalar_type() == at::kFloat && m.scalar_type() == at::kFloat && v.scalar_type() == at::kFloat, "adamw_shard: fp32 state");
   need(is_bf16_cuda(flat_param), "adamw_shard: bf16 flat_param");
   need(segs.is_cuda() && segs.scalar_type() == at::kByte && segs.numel() >= (int64_t)(nseg * sizeof(ZtbSegment)), "adamw_shard: segs");
@@ -207,11 +233,12 @@ void adamw_shard(at::Tensor& master, at::Tensor& m, at::Tensor& v, at::Tensor& f
   a.lr = (float)lr; a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps; a.wd = (float)wd; a.clip = (float)clip;
   a.grad_scale = (float)grad_scale;
   a.scale_mul = reinterpret_cast<const float*>(scale_mul_ptr);
-  a.bc1 = (float)(1.0 - std::pow(beta1, (double)step));
-  a.bc2 = (float)(1.0 - std::pow(beta2, (double)step));
+  a.inv_bc1 = (float)(1.0 / (1.0 - std::pow(beta1, (double)step)));
+  a.inv_bc2 = (float)(1.0 / (1.0 - std::pow(beta2, (double)step)));
+  a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
   check(ztb_adamw_shard(master.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), flat_param.data_ptr(), gp.data(), (int)gp.size(),
                         grad_is_fp32, reinterpret_cast<const ZtbSegment*>(segs.data_ptr()), (int)nseg, total_tiles, a,
-                        reinterpret_cast<const int*>(wait_flags_ptr), (int)wait_value, num_sms(), (int)side_sms, reinterpret_cast<const void*>(mc_grad_ptr),
+                        reinterpret_cast<const int*>(wait_flags_ptr), (int)wait_value, num_sms(), (int)max_ctas, reinterpret_cast<const void*>(mc_grad_ptr),
                         reinterpret_cast<void*>(mc_param_ptr), stream()), "adamw_shard");
 }
 
@@ -292,7 +319,9 @@ void p2p_copy(int64_t dst_ptr, int64_t src_ptr, int64_t bytes) {
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("layernorm_fwd", &layernorm_fwd);
-  m.def("layernorm_bwd", &layernorm_bwd, py::arg("dy"), py::arg("x"), py::arg("w"), py::arg("mean"), py::arg("rstd"), py::arg("dres") = py::none());
+  m.def("layernorm_bwd", &layernorm_bwd, py::arg("dy"), py::arg("x"), py::arg("w"), py::arg("mean"), py::arg("rstd"), py::arg("dres") = py::none(),
+        py::arg("grad_out") = py::none(), py::arg("accumulate") = false, py::arg("scratch") = py::none(), py::arg("ticket") = py::none(),
+        py::arg("drop_p") = 0.0, py::arg("rng") = py::none(), py::arg("op_id") = 0);
   m.def("dropout_add", &dropout_add);
   m.def("embedding_fwd", &embedding_fwd);
   m.def("embedding_bwd_", &embedding_bwd_);
@@ -302,14 +331,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ce_bwd_", &ce_bwd_);
   m.def("gemm", &gemm, py::arg("A"), py::arg("B"), py::arg("C") = py::none(), py::arg("epilogue") = 0, py::arg("aux_in") = py::none(),
         py::arg("aux_out") = py::none(), py::arg("p") = 0.0, py::arg("rng") = py::none(), py::arg("op_id") = 0,
-        py::arg("accumulate") = false, py::arg("a_mn") = false, py::arg("b_mn") = false, py::arg("two_cta") = false, py::arg("no_split") = false);
+        py::arg("accumulate") = false, py::arg("a_mn") = false, py::arg("b_mn") = false, py::arg("two_cta") = false, py::arg("no_split") = false,
+        py::arg("direct_store") = -1, py::arg("raster_n") = -1);
   m.def("gemm_ag", &gemm_ag);
   m.def("adamw_shard", &adamw_shard, py::arg("master"), py::arg("m"), py::arg("v"), py::arg("flat_param"), py::arg("grad_ptrs"),
         py::arg("grad_is_fp32"), py::arg("segs"), py::arg("nseg"), py::arg("total_tiles"), py::arg("lr"), py::arg("beta1"), py::arg("beta2"),
         py::arg("eps"), py::arg("wd"), py::arg("clip"), py::arg("grad_scale"), py::arg("step"), py::arg("wait_flags_ptr") = 0,
-        py::arg("wait_value") = 0, py::arg("side_sms") = 0, py::arg("scale_mul_ptr") = 0, py::arg("mc_grad_ptr") = 0, py::arg("mc_param_ptr") = 0);
-  m.def("set_sm_reserve", [](int64_t n) { g_sm_reserve = n < 0 ? 0 : (int)n; }, "persistent GEMMs leave this many SMs free");
-  m.def("get_sm_reserve", []() { return (int64_t)g_sm_reserve; });
+        py::arg("wait_value") = 0, py::arg("max_ctas") = 0, py::arg("scale_mul_ptr") = 0, py::arg("mc_grad_ptr") = 0, py::arg("mc_param_ptr") = 0);
   m.def("segment_struct_size", &segment_struct_size);
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_bwd", &attention_bwd, py::arg("qkv"), py::arg("out"), py::arg("dout"), py::arg("lse"), py::arg("slopes"), py::arg("H"),

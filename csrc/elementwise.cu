@@ -9,6 +9,10 @@
 
 namespace ztb {
 
+struct LnBwdExtra;
+// Last-block epilogue of LayerNorm backward (shared by the fast and the generic kernel): see layernorm_bwd_kernel.
+ZTB_DEVINL void ln_bwd_finalize(float* dw, int D, const LnBwdExtra& ex, bool* is_last);
+
 // ============================================================== LayerNorm
 // One warp per row, the whole row in registers: D = 256 * NV elements, lane l owns
 // 16-byte vectors v*32 + l  (v < NV).  Stats in fp32.
@@ -54,19 +58,62 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const bf16* __restri
 }
 
 // Backward: dx = rstd * (dy*w - mean(dy*w) - xhat * mean(dy*w*xhat));  dw += sum_rows dy*xhat.
-// Persistent grid: each warp strides over rows and keeps its dw partial in registers; one
-// smem reduction + fp32 atomics per block at the end.
+// Persistent grid: each warp strides over rows and keeps its dw partial in registers; one smem reduction + fp32 atomics
+// per block into a small persistent scratch vector, and the LAST block to finish folds the scratch into the weight's
+// gradient buffer (bf16 or fp32, overwrite or accumulate) and leaves scratch + ticket zeroed for the next launch -- no
+// memset, no separate add/copy kernel (those were 3 launches per LayerNorm backward).
+// Optional second output `dmask`: dropout-masked copy of dx (x is the output of a dropout+residual epilogue, whose
+// backward needs mask(dx)/keep as the operand of its dgrad/wgrad GEMMs): same Philox mapping as dropout_add_kernel.
+struct LnBwdExtra {
+  void* grad_out;        // [D] gradient of the LayerNorm weight
+  int grad_fp32;         // dtype of grad_out
+  int grad_accumulate;   // += instead of =
+  unsigned int* ticket;  // finished-block counter (zero on entry, zero on exit)
+  bf16* dmask;           // optional [M, D]
+  float p, inv_keep;
+  const uint64_t* rng;
+  uint32_t op_id;
+};
+
+ZTB_DEVINL void ln_bwd_finalize(float* dw, int D, const LnBwdExtra& ex, bool* is_last) {
+  if (ex.ticket == nullptr) return;       // caller reads the fp32 scratch itself
+  __threadfence();                        // this block's atomics are performed before its ticket
+  __syncthreads();
+  if (threadIdx.x == 0) *is_last = atomicAdd(ex.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!*is_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = __ldcg(dw + c);
+    dw[c] = 0.f;
+    if (ex.grad_fp32) {
+      float* g = reinterpret_cast<float*>(ex.grad_out) + c;
+      *g = ex.grad_accumulate ? *g + s : s;
+    } else {
+      bf16* g = reinterpret_cast<bf16*>(ex.grad_out) + c;
+      *g = __float2bfloat16(ex.grad_accumulate ? __bfloat162float(*g) + s : s);
+    }
+  }
+  if (threadIdx.x == 0) *ex.ticket = 0u;
+}
+
 template <int NV>
 __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                             const bf16* __restrict__ w, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, bf16* __restrict__ dx,
-                                                            float* __restrict__ dw, int M, const bf16* __restrict__ dres) {
+                                                            float* __restrict__ dw, int M, const bf16* __restrict__ dres,
+                                                            const LnBwdExtra ex) {
   constexpr int D = NV * 256;
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float acc[NV * 8];
 #pragma unroll
   for (int k = 0; k < NV * 8; ++k) acc[k] = 0.f;
   const uint4* wr = reinterpret_cast<const uint4*>(w);
+  const bool drop = ex.dmask != nullptr;
+  uint64_t stream = 0;
+  uint32_t thr = 0;
+  Philox ph(0);
+  if (drop) { ph = Philox(ex.rng[0]); stream = ex.rng[1] * 65536ull + ex.op_id; thr = dropout_threshold(ex.p); }
   for (int row = blockIdx.x * 4 + warp; row < M; row += gridDim.x * 4) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * D);
     const uint4* gr = reinterpret_cast<const uint4*>(dy + (size_t)row * D);
@@ -108,15 +155,28 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
         os[k] = pack_bf16(rs * (gf.x * wf.x - s1 - xh0 * s2) + rf.x, rs * (gf.y * wf.y - s1 - xh1 * s2) + rf.y);
       }
       st_v4(dr + i * 32 + lane, make_uint4(os[0], os[1], os[2], os[3]));
+      if (drop) {  // masked copy of the (bf16-rounded) dx, exactly what dropout_add_kernel<false> would produce from it
+        const size_t vi = (size_t)row * (D / 8) + i * 32 + lane;
+        uint4 r0 = ph.rounds<6>(2 * vi, stream), r1 = ph.rounds<6>(2 * vi + 1, stream);
+        uint32_t rb[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w}, ms[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 df = unpack_bf16(os[k]);
+          ms[k] = pack_bf16(rb[2 * k] >= thr ? df.x * ex.inv_keep : 0.f, rb[2 * k + 1] >= thr ? df.y * ex.inv_keep : 0.f);
+        }
+        st_v4(reinterpret_cast<uint4*>(ex.dmask + (size_t)row * D) + i * 32 + lane, make_uint4(ms[0], ms[1], ms[2], ms[3]));
+      }
     }
   }
   __shared__ float red[4][NV * 256];
+  __shared__ bool is_last;
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
     for (int k = 0; k < 8; ++k) red[warp][(i * 32 + lane) * 8 + k] = acc[i * 8 + k];
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += 128) atomicAdd(dw + c, red[0][c] + red[1][c] + red[2][c] + red[3][c]);
+  ln_bwd_finalize(dw, D, ex, &is_last);
 }
 
 // Generic-D fallback (D not a multiple of 256, e.g. the 64-wide test model): one block per row.
@@ -139,8 +199,10 @@ __global__ void layernorm_fwd_generic(const bf16* __restrict__ x, const bf16* __
 }
 __global__ void layernorm_bwd_generic(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
                                       const float* __restrict__ mean, const float* __restrict__ rstd,
-                                      bf16* __restrict__ dx, float* __restrict__ dw, int M, int D, const bf16* __restrict__ dres) {
+                                      bf16* __restrict__ dx, float* __restrict__ dw, int M, int D, const bf16* __restrict__ dres,
+                                      const LnBwdExtra ex) {
   __shared__ float sh[2][4];
+  __shared__ bool is_last;
   int row = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float mu = mean[row], rs = rstd[row], s1 = 0.f, s2 = 0.f;
   for (int c = threadIdx.x; c < D; c += 128) {
@@ -159,8 +221,17 @@ __global__ void layernorm_bwd_generic(const bf16* __restrict__ dy, const bf16* _
     float xh = (__bfloat162float(x[(size_t)row * D + c]) - mu) * rs;
     float gw = __bfloat162float(dy[(size_t)row * D + c]) * __bfloat162float(w[c]);
     float extra = dres ? __bfloat162float(dres[(size_t)row * D + c]) : 0.f;
-    dx[(size_t)row * D + c] = __float2bfloat16(rs * (gw - s1 - xh * s2) + extra);
+    bf16 o = __float2bfloat16(rs * (gw - s1 - xh * s2) + extra);
+    dx[(size_t)row * D + c] = o;
+    if (ex.dmask != nullptr) {   // same mask as dropout_add_kernel: element e -> Philox counter e / 4, word e % 4
+      const size_t e = (size_t)row * D + c;
+      Philox ph(ex.rng[0]);
+      uint4 r4 = ph.rounds<6>(e >> 2, ex.rng[1] * 65536ull + ex.op_id);
+      uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+      ex.dmask[e] = __float2bfloat16(rw[e & 3] >= dropout_threshold(ex.p) ? __bfloat162float(o) * ex.inv_keep : 0.f);
+    }
   }
+  ln_bwd_finalize(dw, D, ex, &is_last);
 }
 
 // ============================================================== dropout + residual
@@ -364,13 +435,19 @@ int ztb_layernorm_fwd(const void* x, const void* w, void* y, float* mean, float*
 }
 
 int ztb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
-                      float* dw, int M, int D, int sms, cudaStream_t st, const void* dres) {
-  ZTB_CUDA_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * D, st));
+                      float* dw, int M, int D, int sms, cudaStream_t st, const void* dres, const ZtbLnBwdExtra* extra) {
+  LnBwdExtra ex{};
+  if (extra != nullptr) {
+    ex.grad_out = extra->grad_out; ex.grad_fp32 = extra->grad_fp32; ex.grad_accumulate = extra->grad_accumulate;
+    ex.ticket = extra->ticket; ex.dmask = (bf16*)extra->dmask; ex.p = extra->p;
+    ex.inv_keep = extra->p < 1.f ? 1.f / (1.f - extra->p) : 0.f; ex.rng = extra->rng; ex.op_id = extra->op_id;
+  }
+  if (ex.ticket == nullptr) ZTB_CUDA_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * D, st));   // one-shot scratch: caller owns dw
   if (ln_fast(D)) {
     int nv = D / 256, grid = grid_for((M + 3) / 4, 1, sms * 4);
-    LN_DISPATCH(nv, layernorm_bwd_kernel, grid, (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, (const bf16*)dres)
+    LN_DISPATCH(nv, layernorm_bwd_kernel, grid, (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, (const bf16*)dres, ex)
   } else {
-    layernorm_bwd_generic<<<M, 128, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, D, (const bf16*)dres);
+    layernorm_bwd_generic<<<M, 128, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, D, (const bf16*)dres, ex);
   }
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;

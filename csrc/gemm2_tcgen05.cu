@@ -9,6 +9,9 @@
 // (src/models/layers.py:60-77,112-143,180-189), which XLA lowered to MXU dots.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
+
+#include <mutex>
 
 #include "common.cuh"
 #include "launchers.h"
@@ -26,6 +29,9 @@ constexpr int WBUF_BYTES = 32 * 128;         // one warp's staging buffer: 32 ro
 constexpr int CSTAGE_BYTES = EPI_WARPS * 2 * WBUF_BYTES;  // 64 KB: double-buffered per warp
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + CSTAGE_BYTES + 256 + 1024;
 constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
+// Register cap: 12 warps x 128 registers = 48 K of the SM's 64 K, so a 128-thread CTA of the overlapped ZeRO-1 update
+// kernel (<= 64 registers per thread, no shared memory) can be co-resident with a GEMM CTA on every SM.
+constexpr int GEMM_MAX_REGS = 128;
 constexpr int GROUP_M = 8;                   // in 256-row tiles
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
 
@@ -44,6 +50,11 @@ struct GemmParams {
   // bulk reduce-adds (C pre-initialised by the launcher).  split == 1: every tile is one unit.
   int full_tiles, tail, split;
   int* chain;   // split > 1: [tail][16] per-(tile, CTA, epilogue warp) count of K-ranges already reduced into C
+  // Output paths that skip the shared-memory staging (each epilogue thread owns 64 contiguous bytes of one row per
+  // 32-column half): bit 0 = the auxiliary output (pre-activation Z), bit 1 = a non-accumulating bf16 C.
+  int direct;
+  bf16* c_raw; bf16* aux_raw; long long ldc_raw, ld_aux_raw;
+  int raster_n;   // walk tiles in groups of GROUP_M column blocks (vocabulary-sized N: the A panel stays in L2)
 };
 
 struct Unit { int tile, kb0, kb1, partial, part; };
@@ -63,6 +74,14 @@ ZTB_DEVINL bool get_unit(int u, const GemmParams& p, int kblocks, Unit& w) {
 }
 
 ZTB_DEVINL void decode_tile(int t, const GemmParams& p, int& mb, int& nb) {
+  if (p.raster_n) {
+    int per_group = GROUP_M * p.tiles_m;
+    int g = t / per_group, r = t % per_group;
+    int gn = min(GROUP_M, p.tiles_n - g * GROUP_M);
+    nb = g * GROUP_M + r % gn;
+    mb = r / gn;
+    return;
+  }
   int per_group = GROUP_M * p.tiles_n;
   int g = t / per_group, r = t % per_group;
   int gm = min(GROUP_M, p.tiles_m - g * GROUP_M);
@@ -111,8 +130,8 @@ ZTB_DEVINL void mbar_arrive_cta0(uint64_t* bar) {  // arrive on CTA 0's copy of 
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-template <bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
                      const GemmParams p) {
@@ -217,16 +236,23 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp < 8) {
     // ===================================================== epilogue (8 warps per CTA, its 128 rows)
+    // A warp drains two 64-column chunks of its 32 accumulator rows per tile, each in two 32-column halves
+    // (one tcgen05.ld.x32 = 32 live fp32 values per thread), so the epilogue stays well below 128 registers and
+    // the CTA leaves room for a small co-resident CTA of another kernel (the overlapped ZeRO-1 update).
     const int e = warp;                     // 0..7
     const int ew = e & 3;                   // TMEM lane quarter (== warp % 4)
     const int chalf = e >> 2;               // this warp handles 64-column chunks chalf, chalf + 2
     const int row = ew * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
     uint8_t* wbuf = smC + e * 2 * WBUF_BYTES;   // this warp's two staging buffers
-    const uint32_t thr = dropout_threshold(p.p);
-    uint64_t seed = 0, stream = 0;
-    if (p.epi == ZTB_EPI_DROPOUT_ADD) { seed = p.rng[0]; stream = p.rng[1] * 65536ull + p.op_id; }
-    Philox ph(seed);
+    uint32_t thr = 0;
+    uint64_t stream = 0;
+    Philox ph(0);
+    if constexpr (EPI == ZTB_EPI_DROPOUT_ADD) {
+      thr = dropout_threshold(p.p);
+      ph = Philox(p.rng[0]);
+      stream = p.rng[1] * 65536ull + p.op_id;
+    }
     auto arrive_tempty = [&](int a) { if (leader) mbar_arrive(&tempty[a]); else mbar_arrive_cta0(&tempty[a]); };
     int acc = 0; uint32_t acc_phase = 0;
     int cbuf = 0;
@@ -234,12 +260,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int u = pair; get_unit(u, p, kblocks, w); u += num_pairs) {
       int mb, nb; decode_tile(w.tile, p, mb, nb);
       const int m0 = mb * TILE_M + cta_rank * BM, n0 = nb * BN;
-      const bool reduce_c = p.accumulate || w.partial;
-      // K-ranges of a split tile are added into C in K order, so the bf16/fp32 sum is reproducible run to
-      // run: this warp's region of range `part` waits for the same region of range part - 1 (finished by a
-      // different CTA pair, in the same or the previous round -- every CTA is resident, so this cannot deadlock).
+      // K-ranges of a split tile meet in C in K order: range 0 stores (or reduce-adds when the GEMM accumulates),
+      // every later range reduce-adds after the same region of the previous range has landed, so the bf16/fp32 sum
+      // is reproducible run to run and C needs no zero-fill.  The previous range was finished by a different CTA
+      // pair, in the same or the previous round -- every CTA is resident, so this cannot deadlock.
+      const bool reduce_c = p.accumulate || w.part > 0;
       int* chain = w.partial ? p.chain + ((w.tile - p.full_tiles) * 16 + (int)cta_rank * 8 + e) : nullptr;
       const int grow = m0 + row;
+      const bool direct_c = (p.direct & 2) && !p.c_fp32 && !reduce_c && !w.partial;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after_sync();
       if (chain != nullptr && w.part > 0) {
@@ -250,111 +278,137 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         __syncwarp();
       }
       const uint32_t t_acc = tmem_base + lane_addr + acc * BN;
-      // One staging buffer holds 128 B per row: 64 bf16 columns or 32 fp32 columns.  Buffers
-      // alternate; before overwriting one, the issuing thread waits until at most one bulk store
-      // (the other buffer's) is still reading smem.
-      // Each epilogue warp owns its 32 rows of the staging buffer and issues its own bulk stores
+      // One staging buffer holds 128 B per row: 64 bf16 columns or 32 fp32 columns.  Buffers alternate; before
+      // overwriting one, the issuing thread waits until at most one bulk store (the other buffer's) is still
+      // reading smem.  Each epilogue warp owns its 32 rows of the staging buffer and issues its own bulk stores
       // ({64|32} x 32-row boxes), so the only synchronisation is warp-local.
       auto begin_buffer = [&]() {
         if (lane == 0) tma_wait_group_read<1>();
         __syncwarp();
       };
-      auto end_buffer = [&](const CUtensorMap* tm, int col) {
+      auto end_buffer = [&](const CUtensorMap* tm, int col, bool reduce) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           const uint8_t* src = wbuf + cbuf * WBUF_BYTES;
-          if (reduce_c) tma_reduce_add_2d(tm, src, col, m0 + ew * 32);
+          if (reduce) tma_reduce_add_2d(tm, src, col, m0 + ew * 32);
           else tma_store_2d(tm, src, col, m0 + ew * 32);
           tma_commit_group();
         }
         cbuf ^= 1;
       };
-      auto stage_bf16 = [&](const float* v) {  // 64 values -> this thread's swizzled 128-byte row
+      // 16 packed bf16x2 words (32 columns) -> half h of this thread's swizzled 128-byte row
+      auto stage_packed_half = [&](const uint32_t* pk, int h) {
         uint8_t* rowp = wbuf + cbuf * WBUF_BYTES + lane * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 o = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                               pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-          sts_v4(rowp + ((j ^ (row & 7)) << 4), o);
-        }
+        for (int j = 0; j < 4; ++j)
+          sts_v4(rowp + (((h * 4 + j) ^ (row & 7)) << 4), make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
+      };
+      // no staging: this thread owns 32 consecutive columns of one row = 64 contiguous bytes
+      auto store_direct_half = [&](bf16* base, long long ld, const uint32_t* pk, int col) {
+        if (grow >= p.M) return;
+        bf16* dst = base + (size_t)grow * ld + col;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col + 8 * j < p.N) st_v4(dst + 8 * j, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
       };
 #pragma unroll 1
-      for (int c = chalf; c < BN / 64; c += 2) {
-        uint32_t r[64];
-        tmem_ld_32x32b_x32(t_acc + c * 64, r);
-        tmem_ld_32x32b_x32(t_acc + c * 64 + 32, r + 32);
-        tmem_wait_ld();
-        if (c >= BN / 64 - 2) {  // this warp's last TMEM read of the accumulator: hand it back to the MMA warp
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) arrive_tempty(acc);
-        }
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c = chalf + 2 * ci;
         const int gcol = n0 + c * 64;
-        float v[64];
+        uint32_t zp[32];   // GELU with a staged auxiliary output: the packed pre-activation waits for the second buffer
+        if (!p.c_fp32 && !direct_c) begin_buffer();
 #pragma unroll
-        for (int k = 0; k < 64; ++k) v[k] = __uint_as_float(r[k]);
-        if (p.epi == ZTB_EPI_GELU) {
-          if (p.has_aux_out) {  // pre-activation Z leaves through its own tensor map
-            begin_buffer();
-            stage_bf16(v);
-            end_buffer(&tmAux, gcol);
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_acc + c * 64 + h * 32, r);
+          tmem_wait_ld();
+          if (ci == 1 && h == 1) {  // this warp's last TMEM read of the accumulator: hand it back to the MMA warp
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) arrive_tempty(acc);
           }
+          const int hcol = gcol + h * 32;
+          float v[32];
 #pragma unroll
-          for (int k = 0; k < 64; ++k) v[k] = gelu_tanh(v[k]);
-        } else if (p.epi == ZTB_EPI_DROPOUT_ADD || p.epi == ZTB_EPI_GELU_BWD) {
-          const bool in_rows = grow < p.M;
-          const bf16* ap = p.aux_in + (size_t)grow * p.ld_aux + gcol;
+          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+          if constexpr (EPI == ZTB_EPI_GELU) {
+            if (p.has_aux_out) {  // pre-activation Z
+              uint32_t* zq = zp + h * 16;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            uint4 u = make_uint4(0, 0, 0, 0);
-            if (in_rows && gcol + q * 8 < p.N) u = ld_nc_l1_v4(ap + q * 8);
-            uint32_t us[4] = {u.x, u.y, u.z, u.w};
-            if (p.epi == ZTB_EPI_DROPOUT_ADD) {
-              size_t idx = (size_t)grow * p.N + gcol + q * 8;
-              uint4 r0 = ph.rounds<6>(idx >> 2, stream), r1 = ph.rounds<6>((idx >> 2) + 1, stream);
-              uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+              for (int k = 0; k < 16; ++k) zq[k] = pack_bf16(v[2 * k], v[2 * k + 1]);
+              if (p.direct & 1) store_direct_half(p.aux_raw, p.ld_aux_raw, zq, hcol);
+            }
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                float2 rf = unpack_bf16(us[k]);
-                float a = rr[2 * k] >= thr ? v[q * 8 + 2 * k] * p.inv_keep : 0.f;
-                float b = rr[2 * k + 1] >= thr ? v[q * 8 + 2 * k + 1] * p.inv_keep : 0.f;
-                v[q * 8 + 2 * k] = rf.x + a;
-                v[q * 8 + 2 * k + 1] = rf.y + b;
-              }
-            } else {
+            for (int k = 0; k < 32; ++k) v[k] = gelu_tanh(v[k]);
+          } else if constexpr (EPI == ZTB_EPI_DROPOUT_ADD || EPI == ZTB_EPI_GELU_BWD) {
+            const bool in_rows = grow < p.M;
+            const bf16* ap = p.aux_in + (size_t)grow * p.ld_aux + hcol;
+            uint4 au[4];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                float2 zf = unpack_bf16(us[k]);
-                v[q * 8 + 2 * k] *= gelu_tanh_grad(zf.x);
-                v[q * 8 + 2 * k + 1] *= gelu_tanh_grad(zf.y);
+            for (int q = 0; q < 4; ++q) {
+              au[q] = make_uint4(0, 0, 0, 0);
+              if (in_rows && hcol + q * 8 < p.N) au[q] = ld_nc_l1_v4(ap + q * 8);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t us[4] = {au[q].x, au[q].y, au[q].z, au[q].w};
+              if constexpr (EPI == ZTB_EPI_DROPOUT_ADD) {
+                size_t idx = (size_t)grow * p.N + hcol + q * 8;
+                uint4 r0 = ph.rounds<6>(idx >> 2, stream), r1 = ph.rounds<6>((idx >> 2) + 1, stream);
+                uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float2 rf = unpack_bf16(us[k]);
+                  float a = rr[2 * k] >= thr ? v[q * 8 + 2 * k] * p.inv_keep : 0.f;
+                  float b = rr[2 * k + 1] >= thr ? v[q * 8 + 2 * k + 1] * p.inv_keep : 0.f;
+                  v[q * 8 + 2 * k] = rf.x + a;
+                  v[q * 8 + 2 * k + 1] = rf.y + b;
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float2 zf = unpack_bf16(us[k]);
+                  v[q * 8 + 2 * k] *= gelu_tanh_grad(zf.x);
+                  v[q * 8 + 2 * k + 1] *= gelu_tanh_grad(zf.y);
+                }
               }
             }
           }
-        }
-        if (p.c_fp32) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          if (p.c_fp32) {   // 32 fp32 columns fill a 128-byte row: one buffer and one bulk store per half
             begin_buffer();
             uint8_t* rowp = wbuf + cbuf * WBUF_BYTES + lane * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float* s4 = v + h * 32 + 4 * j;
-              uint4 o = make_uint4(__float_as_uint(s4[0]), __float_as_uint(s4[1]), __float_as_uint(s4[2]), __float_as_uint(s4[3]));
-              sts_v4(rowp + ((j ^ (row & 7)) << 4), o);
-            }
-            end_buffer(&tmC, gcol + h * 32);
+            for (int j = 0; j < 8; ++j)
+              sts_v4(rowp + ((j ^ (row & 7)) << 4), make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                                __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+            end_buffer(&tmC, hcol, reduce_c);
+          } else {
+            uint32_t pk[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) pk[k] = pack_bf16(v[2 * k], v[2 * k + 1]);
+            if (direct_c) store_direct_half(p.c_raw, p.ldc_raw, pk, hcol);
+            else stage_packed_half(pk, h);
           }
-        } else {
-          begin_buffer();
-          stage_bf16(v);
-          end_buffer(&tmC, gcol);
+        }
+        if (!p.c_fp32 && !direct_c) end_buffer(&tmC, gcol, reduce_c);
+        if constexpr (EPI == ZTB_EPI_GELU) {
+          if (p.has_aux_out && !(p.direct & 1)) {   // the pre-activation leaves through its own tensor map
+            begin_buffer();
+            stage_packed_half(zp, 0);
+            stage_packed_half(zp + 16, 1);
+            end_buffer(&tmAux, gcol, false);
+          }
         }
       }
-      if (chain != nullptr && w.part + 1 < p.split && lane == 0) {
-        tma_wait_group<0>();            // this range's reduce-adds have been performed ...
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        st_release_gpu(chain, w.part + 1);  // ... the next range of this region may go
+      if (chain != nullptr && lane == 0) {
+        if (w.part + 1 < p.split) {
+          tma_wait_group<0>();            // this range's stores / reduce-adds have been performed ...
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          st_release_gpu(chain, w.part + 1);  // ... the next range of this region may go
+        } else {
+          *chain = 0;                     // last range: leave the counter ready for the next launch that uses this slot
+        }
       }
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
@@ -377,10 +431,10 @@ using namespace ztb;
 int ztb_make_tmap_2d(CUtensorMap* tm, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
                      int box_cols, int box_rows);
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int EPI>
 static int launch2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& x, const g2::GemmParams& p,
                    int grid, cudaStream_t st) {
-  auto kern = g2::gemm2_tcgen05_kernel<A_MN, B_MN>;
+  auto kern = g2::gemm2_tcgen05_kernel<A_MN, B_MN, EPI>;
   static bool configured = false;
   if (!configured) {
     ZTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g2::GEMM_SMEM));
@@ -391,10 +445,39 @@ static int launch2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap
   return 0;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// K-split ordering counters: one slot of a small per-device ring per launch.  The kernel leaves every counter it
+// used at zero again (the last K-range resets it), so the ring is zeroed once, at allocation.
+static int* chain_slot(int* err) {
+  constexpr int kSlotInts = 128 * 16, kSlots = 64, kMaxDev = 16;
+  static std::mutex mu;
+  static int* ring[kMaxDev] = {nullptr};
+  static unsigned next_slot[kMaxDev] = {0};
+  *err = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) { *err = -1; return nullptr; }
+  std::lock_guard<std::mutex> lock(mu);
+  if (ring[dev] == nullptr) {
+    if (cudaMalloc(&ring[dev], sizeof(int) * kSlotInts * kSlots) != cudaSuccess ||
+        cudaMemset(ring[dev], 0, sizeof(int) * kSlotInts * kSlots) != cudaSuccess) { ring[dev] = nullptr; *err = -1; return nullptr; }
+  }
+  return ring[dev] + (size_t)(next_slot[dev]++ % kSlots) * kSlotInts;
+}
+
 // Same contract as ztb_gemm (without the all-gather variant); M is processed in 256-row tiles.
+// Returns -2 (no error message) for an (operand major, epilogue) combination this kernel is not instantiated for;
+// the caller then uses the general 1-CTA kernel.
 int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
   using namespace g2;
   if (g->M <= 0 || g->N <= 0 || g->K <= 0) return 0;
+  const int major = (g->a_mn_major ? 2 : 0) | (g->b_mn_major ? 1 : 0);
+  const bool supported = g->epilogue == ZTB_EPI_NONE || (major == 0 && (g->epilogue == ZTB_EPI_GELU || g->epilogue == ZTB_EPI_DROPOUT_ADD)) ||
+                         (major == 1 && g->epilogue == ZTB_EPI_GELU_BWD);
+  if (!supported) return -2;
   if ((g->lda % 8) || (g->ldb % 8) || (g->ldc % (g->c_is_fp32 ? 4 : 8)) || (g->K % 8) || (g->N % 8)) {
     ztb_set_error("ztb_gemm_2cta", "leading dimensions / K / N must be multiples of 8 elements", __FILE__, __LINE__);
     return -1;
@@ -424,9 +507,17 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
   if ((g->epilogue == ZTB_EPI_DROPOUT_ADD || g->epilogue == ZTB_EPI_GELU_BWD) && g->aux_in == nullptr) {
     ztb_set_error("ztb_gemm_2cta", "epilogue needs aux_in", __FILE__, __LINE__); return -1;
   }
+  static const int direct_default = env_int("ZTB_GEMM_DIRECT", 0);
+  p.direct = g->direct_store >= 0 ? g->direct_store : direct_default;
+  p.c_raw = (bf16*)g->C; p.ldc_raw = g->ldc; p.aux_raw = (bf16*)g->aux_out; p.ld_aux_raw = g->ld_aux;
   p.p = g->p; p.inv_keep = g->p < 1.f ? 1.f / (1.f - g->p) : 0.f;
   p.rng = g->rng; p.op_id = g->op_id;
   p.tiles_m = (g->M + TILE_M - 1) / TILE_M; p.tiles_n = (g->N + BN - 1) / BN; p.num_tiles = p.tiles_m * p.tiles_n;
+  // Raster: groups of GROUP_M row blocks sweep all column blocks (B panel streams, A group stays hot) -- unless N is
+  // vocabulary-sized: then groups of column blocks sweep all row blocks, so the 10^2 MB activation panel is re-read
+  // from L2 and the weight streams through once.
+  static const int raster_env = env_int("ZTB_GEMM_RASTER_N", -1);
+  p.raster_n = g->raster_n >= 0 ? g->raster_n : (raster_env >= 0 ? raster_env : (p.tiles_n > 4 * p.tiles_m ? 1 : 0));
   int pairs = sms / 2;
   // Wave quantisation: num_tiles is rarely a multiple of the 74 CTA pairs (weight gradients: 64 / 192 / 256
   // tiles).  Cut each tile of the last, partial wave into `split` K-ranges so that it costs
@@ -439,27 +530,24 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
       float cost = (float)((p.tail * sp + pairs - 1) / pairs) / sp + 0.03f * (sp - 1);  // + per-unit epilogue/ramp overhead (measured: 8-way split of a 64-tile problem gains nothing)
       if (cost < best - 1e-6f) { best = cost; p.split = sp; }
     }
-    if (p.split > 1 && !g->accumulate)   // partial sums meet in C through reduce-adds: start from zero
-      ZTB_CUDA_CHECK(cudaMemset2DAsync(g->C, (size_t)g->ldc * (g->c_is_fp32 ? 4 : 2), 0, (size_t)g->N * (g->c_is_fp32 ? 4 : 2), g->M, st));
   }
   p.chain = nullptr;
   if (p.split > 1) {
-    // ordering counters: one slot of a small per-device ring per launch, zeroed in-stream
-    constexpr int kSlotInts = 128 * 16, kSlots = 64;
-    static int* ring[16] = {nullptr};
-    static unsigned next_slot = 0;
-    int dev = 0;
-    ZTB_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) { ztb_set_error("ztb_gemm_2cta", "device index out of range", __FILE__, __LINE__); return -1; }
-    if (ring[dev] == nullptr) ZTB_CUDA_CHECK(cudaMalloc(&ring[dev], sizeof(int) * kSlotInts * kSlots));
-    p.chain = ring[dev] + (size_t)(next_slot++ % kSlots) * kSlotInts;
-    ZTB_CUDA_CHECK(cudaMemsetAsync(p.chain, 0, sizeof(int) * p.tail * 16, st));
+    int err = 0;
+    p.chain = chain_slot(&err);
+    if (err) { ztb_set_error("ztb_gemm_2cta", "could not allocate the K-split ordering counters", __FILE__, __LINE__); return -1; }
   }
   const int units = p.full_tiles + p.tail * p.split;
   if (units < pairs) pairs = units;
   int grid = pairs * 2;
-  if (g->a_mn_major && g->b_mn_major) return launch2<true, true>(ta, tb, tc, tx, p, grid, st);
-  if (g->a_mn_major) return launch2<true, false>(ta, tb, tc, tx, p, grid, st);
-  if (g->b_mn_major) return launch2<false, true>(ta, tb, tc, tx, p, grid, st);
-  return launch2<false, false>(ta, tb, tc, tx, p, grid, st);
+  switch (major * 4 + g->epilogue) {
+    case 0 * 4 + ZTB_EPI_NONE: return launch2<false, false, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
+    case 0 * 4 + ZTB_EPI_GELU: return launch2<false, false, ZTB_EPI_GELU>(ta, tb, tc, tx, p, grid, st);
+    case 0 * 4 + ZTB_EPI_DROPOUT_ADD: return launch2<false, false, ZTB_EPI_DROPOUT_ADD>(ta, tb, tc, tx, p, grid, st);
+    case 1 * 4 + ZTB_EPI_NONE: return launch2<false, true, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
+    case 1 * 4 + ZTB_EPI_GELU_BWD: return launch2<false, true, ZTB_EPI_GELU_BWD>(ta, tb, tc, tx, p, grid, st);
+    case 2 * 4 + ZTB_EPI_NONE: return launch2<true, false, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
+    case 3 * 4 + ZTB_EPI_NONE: return launch2<true, true, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
+  }
+  return -2;
 }

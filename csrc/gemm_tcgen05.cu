@@ -438,7 +438,10 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
 
 int ztb_gemm(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
   if (g->M <= 0 || g->N <= 0 || g->K <= 0) return 0;
-  if (g->two_cta && !g->ag) return ztb_gemm_2cta(g, sms, st);
+  if (g->two_cta && !g->ag) {
+    const int rc2 = ztb_gemm_2cta(g, sms, st);
+    if (rc2 != -2) return rc2;   // -2: that (operand major, epilogue) pair only exists in this general kernel
+  }
   if ((g->lda % 8) || (g->ldb % 8) || (g->ldc % (g->c_is_fp32 ? 4 : 8)) || (g->K % 8) || (g->N % 8)) {
     ztb_set_error("ztb_gemm", "leading dimensions / K / N must be multiples of 8 elements (16-byte TMA strides)", __FILE__, __LINE__);
     return -1;

@@ -10,8 +10,16 @@ const char* ztb_last_error();
 
 // ---- elementwise.cu
 int ztb_layernorm_fwd(const void* x, const void* w, void* y, float* mean, float* rstd, int M, int D, float eps, cudaStream_t st);
+// Optional extras of LayerNorm backward.  With `ticket` set, `dw` is a persistent zeroed fp32 scratch vector: the last
+// block folds it into `grad_out` (overwrite or accumulate) and re-zeroes scratch and ticket.  `dmask`: second output,
+// dropout-masked copy of dx (mask of the dropout+residual op that produced the LayerNorm input).
+struct ZtbLnBwdExtra {
+  void* grad_out; int grad_fp32; int grad_accumulate; unsigned int* ticket;
+  void* dmask; float p; const uint64_t* rng; uint32_t op_id;
+};
 int ztb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
-                      float* dw, int M, int D, int sms, cudaStream_t st, const void* dres = nullptr);
+                      float* dw, int M, int D, int sms, cudaStream_t st, const void* dres = nullptr,
+                      const ZtbLnBwdExtra* extra = nullptr);
 int ztb_dropout_add(const void* y, const void* res, void* out, size_t n, float p, const uint64_t* rng, uint32_t op_id,
                     int sms, cudaStream_t st);
 int ztb_embedding_fwd(const int* idx, const void* wte, void* out, int M, int D, int V, cudaStream_t st);
@@ -32,13 +40,15 @@ struct ZtbSegment {      // one parameter region's chunk owned by this rank
   int pad;
 };
 struct ZtbAdamArgs {
-  float lr, beta1, beta2, eps, wd, clip, grad_scale, bc1, bc2;
+  float lr, beta1, beta2, eps, wd, clip, grad_scale;
+  float inv_bc1, inv_bc2;   // 1 / (1 - beta^step): bias corrections, reciprocal (the kernel multiplies)
+  float omb1, omb2;         // 1 - beta1, 1 - beta2
   const float* scale_mul;   // optional device scalar multiplied into grad_scale (global-norm clip coefficient)
 };
 // grads[p] = flat grad buffer of peer p (p = 0 is local); n_peers == 1 -> plain fused AdamW.
 int ztb_adamw_shard(float* master, float* m, float* v, void* flat_param, const void* const* grads, int n_peers,
                     int grad_is_fp32, const ZtbSegment* segs, int nseg, long long total_tiles, ZtbAdamArgs a,
-                    const int* wait_flags, int wait_value, int sms, int side_sms, const void* mc_grad, void* mc_param,
+                    const int* wait_flags, int wait_value, int sms, int max_ctas, const void* mc_grad, void* mc_param,
                     cudaStream_t st);
 
 // ---- gemm_tcgen05.cu
@@ -65,6 +75,8 @@ struct ZtbGemmArgs {
   const ZtbAgArgs* ag;                      // non-null: gather B's remote row chunks inside the kernel
   int two_cta;                              // use the cta_group::2 (256x256 per CTA pair) kernel
   int no_split;                             // two_cta: disable K-splitting of the last partial wave
+  int direct_store;                         // two_cta: -1 default (ZTB_GEMM_DIRECT), else bit 0 aux output / bit 1 C skip smem staging
+  int raster_n;                             // two_cta: -1 auto, 0 row-block groups, 1 column-block groups (vocabulary-sized N)
 };
 int ztb_gemm_2cta(const ZtbGemmArgs* args, int sms, cudaStream_t st);
 int ztb_gemm(const ZtbGemmArgs* args, int sms, cudaStream_t st);

@@ -305,3 +305,143 @@ def test_gemm_2cta_epilogues(K):
     K._C.gemm(dy, x, C=c1, accumulate=True, a_mn=True, b_mn=True, two_cta=False)
     K._C.gemm(dy, x, C=c2, accumulate=True, a_mn=True, b_mn=True, two_cta=True)
     torch.testing.assert_close(c1, c2, rtol=1e-5, atol=1e-3)
+
+
+# ------------------------------------------------------------------ round-2 kernel features
+@pytest.mark.parametrize("direct", [0, 1, 2, 3])
+def test_gemm_2cta_direct_store_paths_are_bitwise_equal(K, direct):
+    """Outputs that skip the shared-memory staging (st.global from registers) must equal the TMA-store path bit for bit."""
+    M, N, Kd = 520, 1032, 512          # ragged M and N: exercises the row / column guards of the direct path
+    a, b, res = _rand(M, Kd, scale=0.5), _rand(N, Kd, scale=0.05), _rand(M, N)
+    rng = K.rng_state("cuda")
+    z0 = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    z1 = torch.zeros_like(z0)
+    g0 = K._C.gemm(a, b, epilogue=K.EPI_GELU, aux_out=z0, two_cta=True, direct_store=0)
+    g1 = K._C.gemm(a, b, epilogue=K.EPI_GELU, aux_out=z1, two_cta=True, direct_store=direct)
+    assert torch.equal(g0, g1) and torch.equal(z0, z1)
+    d0 = K._C.gemm(a, b, epilogue=K.EPI_DROPOUT_ADD, aux_in=res, p=0.25, rng=rng, op_id=5, two_cta=True, direct_store=0)
+    d1 = K._C.gemm(a, b, epilogue=K.EPI_DROPOUT_ADD, aux_in=res, p=0.25, rng=rng, op_id=5, two_cta=True, direct_store=direct)
+    assert torch.equal(d0, d1)
+    p0 = K._C.gemm(a, b, two_cta=True, direct_store=0)
+    p1 = K._C.gemm(a, b, two_cta=True, direct_store=direct)
+    assert torch.equal(p0, p1)
+    _close(p0, a.float() @ b.float().t(), atol=2e-2 * math.sqrt(Kd))
+
+
+@pytest.mark.parametrize("raster_n", [0, 1])
+def test_gemm_2cta_raster_orders_agree(K, raster_n):
+    a, b = _rand(768, 256), _rand(5000 * 8, 256, scale=0.1)     # vocabulary-shaped N
+    c = K._C.gemm(a, b, two_cta=True, raster_n=raster_n)
+    _close(c, a.float() @ b.float().t(), atol=2e-2 * 16)
+
+
+@pytest.mark.parametrize("cdtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_gemm_2cta_ksplit_tail_needs_no_zero_fill_and_resets_its_counters(K, cdtype, accumulate):
+    """A weight-gradient shape whose tiles do not fill a wave is K-split; range 0 stores, later ranges reduce-add in
+    order.  C starts as garbage (no memset in the launcher) and the ordering counters must be reusable launch after launch."""
+    M, N, Kd = 4096, 1024, 512     # dW[N, Kd] = dY^T X: 4 x 2 tiles of 256x256, K = 4096 -> split
+    dy, x = _rand(M, N, scale=0.5), _rand(M, Kd, scale=0.5)
+    ref = dy.float().t() @ x.float()
+    outs = []
+    for it in range(3):
+        c0 = torch.randn(N, Kd, device="cuda").to(cdtype)
+        c = c0.clone()
+        K._C.gemm(dy, x, C=c, accumulate=accumulate, a_mn=True, b_mn=True, two_cta=True)
+        want = ref + (c0.float() if accumulate else 0)
+        _close(c, want, rtol=2e-2, atol=1.0 if cdtype == torch.bfloat16 else 0.5)
+        outs.append((c.float() - (c0.float() if accumulate else 0)).clone())
+    if cdtype == torch.float32 and not accumulate:
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])   # ordered reduction: reproducible
+
+
+@pytest.mark.parametrize("D", [64, 768, 2048])
+@pytest.mark.parametrize("gdtype", [torch.bfloat16, torch.float32])
+def test_layernorm_bwd_writes_weight_grad_in_kernel(K, D, gdtype):
+    M = 300
+    x, dy, dres = _rand(M, D), _rand(M, D), _rand(M, D)
+    w = (1 + 0.1 * torch.randn(D, device="cuda")).to(torch.bfloat16)
+    y, mean, rstd = K._C.layernorm_fwd(x, w, 1e-5)
+    dx0, dw0, _ = K._C.layernorm_bwd(dy, x, w, mean, rstd, dres)          # legacy path: fp32 dw returned
+    scratch = torch.zeros(D, dtype=torch.float32, device="cuda")
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    g = torch.full((D,), 7.0, device="cuda").to(gdtype)
+    for rep in range(2):   # overwrite, twice: scratch / ticket must come back zeroed
+        dx1, dw1, dm = K._C.layernorm_bwd(dy, x, w, mean, rstd, dres, grad_out=g, accumulate=False, scratch=scratch, ticket=ticket)
+        assert torch.equal(dx0, dx1) and dw1.numel() == 0 and dm.numel() == 0
+        _close(g, dw0, rtol=2e-2, atol=0.3 if gdtype == torch.bfloat16 else 1e-2)
+        assert int(ticket.item()) == 0 and float(scratch.abs().max()) == 0.0
+    before = g.float().clone()
+    K._C.layernorm_bwd(dy, x, w, mean, rstd, dres, grad_out=g, accumulate=True, scratch=scratch, ticket=ticket)
+    _close(g, before + dw0, rtol=2e-2, atol=0.6 if gdtype == torch.bfloat16 else 1e-2)
+
+
+@pytest.mark.parametrize("D", [64, 2048])
+def test_layernorm_bwd_masked_second_output_equals_dropout_kernel(K, D):
+    M = 256
+    x, dy = _rand(M, D), _rand(M, D)
+    w = torch.ones(D, device="cuda", dtype=torch.bfloat16)
+    _, mean, rstd = K._C.layernorm_fwd(x, w, 1e-5)
+    rng = K.rng_state("cuda")
+    dx, _, dm = K._C.layernorm_bwd(dy, x, w, mean, rstd, None, drop_p=0.3, rng=rng, op_id=11)
+    want = K._C.dropout_add(dx, None, 0.3, rng, 11)
+    assert torch.equal(dm, want)
+    assert abs((dm.float() == 0).float().mean().item() - 0.3) < 0.03
+
+
+def test_dropout_backward_is_served_by_layernorm_backward(K, monkeypatch):
+    """residual + dropout(linear) -> LayerNorm: in backward the dropout mask must come out of the LayerNorm-backward kernel
+    (no dropout_add launch) and give the same gradients as the standalone kernel."""
+    import zero_transformer_b200.ops.cuda as C
+
+    D = 512
+    torch.manual_seed(5)
+    x = _rand(4, 64, D).requires_grad_(True)
+    w = _rand(D, D, scale=0.05).requires_grad_(True)
+    lnw = torch.ones(D, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    res = _rand(4, 64, D).requires_grad_(True)
+    up = _rand(4, 64, D)
+
+    def run(fold):
+        monkeypatch.setattr(C.CONFIG, "fold_dropout_bwd", fold)
+        for t in (x, w, lnw, res):
+            t.grad = None
+        C.manual_seed(77)
+        C.begin_forward("cuda")
+        calls = {"n": 0}
+        real = C._C.dropout_add
+
+        def counting(*a, **k):
+            calls["n"] += 1
+            return real(*a, **k)
+
+        monkeypatch.setattr(C._C, "dropout_add", counting)
+        out = C.linear_dropout_add(x, w, res, 0.2, True)
+        y, xr = C.layernorm_res(out, lnw, 1e-5)
+        (y * up + xr).sum().backward()
+        monkeypatch.setattr(C._C, "dropout_add", real)
+        return calls["n"], [t.grad.clone() for t in (x, w, lnw, res)]
+
+    n_fold, g_fold = run(True)
+    n_plain, g_plain = run(False)
+    assert n_fold == 0 and n_plain == 1
+    for a, b in zip(g_fold, g_plain):
+        assert torch.equal(a, b)
+
+
+def test_fused_adamw_background_shape_matches_wide(K):
+    from zero_transformer_b200.parallel.fused import pack_segments
+
+    n = 1024 * 37 + 64
+    grad = _rand(n, scale=2.0)
+    segs, tiles = pack_segments([(0, 0, n, True)], "cuda")
+    outs = []
+    for max_ctas in (0, 148, 3):
+        master = torch.linspace(-1, 1, n, device="cuda")
+        m, v = torch.zeros_like(master), torch.zeros_like(master)
+        fp = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+        K._C.adamw_shard(master, m, v, fp, [grad.data_ptr()], False, segs, 1, tiles, 1e-2, 0.9, 0.95, 1e-8, 0.1, 1.0, 0.5, 1, 0, 0, max_ctas)
+        outs.append((master.clone(), m.clone(), v.clone(), fp.clone()))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert torch.equal(a, b)

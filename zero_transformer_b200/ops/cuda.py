@@ -77,6 +77,7 @@ class _Config:
     fuse_wgrad = os.environ.get("ZTB_FUSE_WGRAD", "1") == "1"    # accumulate dW into param.grad in the epilogue
     gemm_2cta = os.environ.get("ZTB_GEMM_2CTA", "1") == "1"      # cta_group::2 256x256 kernel for the big GEMMs
     attn_impl = os.environ.get("ZTB_ATTN", "auto")                # auto | tc (own kernel) | flash (flash_attn library) | ref
+    fold_dropout_bwd = os.environ.get("ZTB_FOLD_DROPOUT_BWD", "1") == "1"  # LayerNorm-backward emits the masked gradient
 
 
 CONFIG = _Config()
@@ -157,29 +158,97 @@ def _mm_dgrad(dy: torch.Tensor, w: torch.Tensor, **kw) -> torch.Tensor:
 
 
 def _mm_wgrad(dy: torch.Tensor, x2: torch.Tensor, w: torch.Tensor) -> Optional[torch.Tensor]:
-    """dW[N,K] = dY[M,N]^T @ X[M,K].  When ``w.grad`` already exists (the ZeRO-1 flat gradient
-    buffer) the product is accumulated into it inside the GEMM epilogue and ``None`` is returned."""
+    """dW[N,K] = dY[M,N]^T @ X[M,K].  When the parameter has a gradient buffer (the ZeRO-1 flat gradient buffer, bf16, or
+    the engine's fp32 main-gradient buffer) the product is written / accumulated into it inside the GEMM epilogue
+    (TMA store or reduce-add) and ``None`` is returned."""
     M, N = dy.shape
     K = x2.shape[1]
     tc = CONFIG.tc_gemm_bwd and _tc_ok(N, K, M) and N % 8 == 0
-    if CONFIG.fuse_wgrad and w.grad is not None and w.grad.is_contiguous():
+    tgt = _grad_target(w)
+    if tgt is not None:
         acc = GRAD_MODE["accumulate"]
         if tc:
-            _C.gemm(dy, x2, C=w.grad, accumulate=acc, a_mn=True, b_mn=True)
+            _C.gemm(dy, x2, C=tgt, accumulate=acc, a_mn=True, b_mn=True)
         elif acc:
-            w.grad.addmm_(dy.t(), x2) if w.grad.dtype == dy.dtype else w.grad.add_((dy.t() @ x2).to(w.grad.dtype))
+            tgt.addmm_(dy.t(), x2) if tgt.dtype == dy.dtype else tgt.add_((dy.t() @ x2).to(tgt.dtype))
         else:
-            w.grad.copy_(dy.t() @ x2)
+            tgt.copy_(dy.t() @ x2)
         return None
     if tc:
         return _C.gemm(dy, x2, a_mn=True, b_mn=True)
     return dy.t() @ x2
 
 
+# ---------------------------------------------------------------------------
+# Dropout backward without its own kernel.  ``residual + dropout(y)`` epilogues hand their output to a LayerNorm;
+# in backward that LayerNorm's kernel produces dx, which is exactly the ``dout`` whose masked copy the epilogue op's
+# dgrad / wgrad GEMMs need.  The LayerNorm-backward kernel therefore emits mask(dx) / keep as a second output
+# (one extra store instead of a read + write + launch): the forward op leaves a note (``_LAST_DROP``), the LayerNorm
+# forward that consumes the tensor picks it up, its backward stashes the masked gradient under the op id.
+_LAST_DROP = {"ptr": 0, "numel": 0, "p": 0.0, "op_id": 0}
+_DROP_STASH = {}
+
+
+def _note_dropout_output(out: torch.Tensor, p: float, op_id: int) -> None:
+    if p > 0.0 and CONFIG.fold_dropout_bwd:
+        _LAST_DROP.update(ptr=out.data_ptr(), numel=out.numel(), p=float(p), op_id=int(op_id))
+
+
+def _claim_dropout_note(x: torch.Tensor):
+    note = None
+    if _LAST_DROP["ptr"] and _LAST_DROP["ptr"] == x.data_ptr() and _LAST_DROP["numel"] == x.numel():
+        note = (_LAST_DROP["p"], _LAST_DROP["op_id"])
+    _LAST_DROP["ptr"] = 0
+    return note
+
+
 def _dropout_bwd(dout2: torch.Tensor, p: float, training: bool, op_id: int, rng: torch.Tensor) -> torch.Tensor:
     if not training or p <= 0.0:
         return dout2
+    hit = _DROP_STASH.pop(op_id, None)
+    if hit is not None and hit[0] == dout2.data_ptr() and hit[1].numel() == dout2.numel():
+        return hit[1].view(dout2.shape)
     return _C.dropout_add(dout2, None, p, rng, op_id)
+
+
+_LN_SCRATCH = {}
+
+
+def _ln_scratch(device: torch.device, D: int):
+    """Persistent (fp32 [D], int32 [1]) scratch of the LayerNorm-backward weight-gradient reduction; the kernel leaves
+    both zeroed.  One pair per (device, stream, D): launches on one stream are serialised."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, D)
+    if key not in _LN_SCRATCH:
+        _LN_SCRATCH[key] = (torch.zeros(D, dtype=torch.float32, device=device), torch.zeros(1, dtype=torch.int32, device=device))
+    return _LN_SCRATCH[key]
+
+
+def _grad_target(w: torch.Tensor):
+    """Where a parameter's gradient is written by the fused paths: the engine's fp32 main-gradient view if it set one,
+    else the (flat-buffer) ``.grad``."""
+    if not CONFIG.fuse_wgrad:
+        return None
+    mg = getattr(w, "_ztb_main_grad", None)
+    if mg is not None:
+        return mg
+    g = w.grad
+    return g if (g is not None and g.is_contiguous()) else None
+
+
+def _ln_backward(ctx, dy, dres):
+    x, w, mean, rstd = ctx.saved_tensors
+    dr = dres.contiguous() if dres is not None else None
+    tgt = _grad_target(w)
+    kw = {}
+    if tgt is not None:
+        scratch, ticket = _ln_scratch(x.device, x.shape[-1])
+        kw.update(grad_out=tgt, accumulate=GRAD_MODE["accumulate"], scratch=scratch, ticket=ticket)
+    if ctx.drop is not None:
+        kw.update(drop_p=ctx.drop[0], rng=rng_state(x.device), op_id=ctx.drop[1])
+    dx, dw, dmask = _C.layernorm_bwd(dy.contiguous(), x, w.contiguous(), mean, rstd, dr, **kw)
+    if ctx.drop is not None:
+        _DROP_STASH[ctx.drop[1]] = (dx.data_ptr(), dmask)
+    return dx, (None if tgt is not None else dw.to(w.dtype))
 
 
 # ---------------------------------------------------------------------------
@@ -187,21 +256,15 @@ class _LayerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, eps):
         xc = x.contiguous()
+        ctx.drop = _claim_dropout_note(xc)
         y, mean, rstd = _C.layernorm_fwd(xc, w.contiguous(), eps)
         ctx.save_for_backward(xc, w, mean, rstd)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, mean, rstd = ctx.saved_tensors
-        dx, dw = _C.layernorm_bwd(dy.contiguous(), x, w.contiguous(), mean, rstd)
-        if CONFIG.fuse_wgrad and w.grad is not None:
-            if GRAD_MODE["accumulate"]:
-                w.grad.add_(dw)
-            else:
-                w.grad.copy_(dw)
-            return dx, None, None
-        return dx, dw.to(w.dtype), None
+        dx, dw = _ln_backward(ctx, dy, None)
+        return dx, dw, None
 
 
 def layernorm(x, weight, eps):
@@ -216,22 +279,15 @@ class _LayerNormRes(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, eps):
         xc = x.contiguous()
+        ctx.drop = _claim_dropout_note(xc)
         y, mean, rstd = _C.layernorm_fwd(xc, w.contiguous(), eps)
         ctx.save_for_backward(xc, w, mean, rstd)
         return y, xc.view_as(xc)
 
     @staticmethod
     def backward(ctx, dy, dres):
-        x, w, mean, rstd = ctx.saved_tensors
-        dr = dres.contiguous() if dres is not None else None
-        dx, dw = _C.layernorm_bwd(dy.contiguous(), x, w.contiguous(), mean, rstd, dr)
-        if CONFIG.fuse_wgrad and w.grad is not None:
-            if GRAD_MODE["accumulate"]:
-                w.grad.add_(dw)
-            else:
-                w.grad.copy_(dw)
-            return dx, None, None
-        return dx, dw.to(w.dtype), None
+        dx, dw = _ln_backward(ctx, dy, dres)
+        return dx, dw, None
 
 
 def layernorm_res(x, weight, eps):
@@ -280,6 +336,7 @@ class _LinearDropoutAdd(torch.autograd.Function):
             out = _C.dropout_add(y, r2.contiguous(), pe, rng, op_id) if y.numel() % 8 == 0 else r2 + y
         ctx.save_for_backward(x2, w)
         ctx.meta = (x.shape, pe, op_id)
+        _note_dropout_output(out, pe, op_id)
         return out.view(residual.shape)
 
     @staticmethod
@@ -325,6 +382,7 @@ class _MLP(torch.autograd.Function):
             out = _C.dropout_add(y, r2.contiguous(), pe, rng, op_id) if y.numel() % 8 == 0 else r2 + y
         ctx.save_for_backward(x2, w1, w2, z, g)
         ctx.meta = (x.shape, pe, op_id)
+        _note_dropout_output(out, pe, op_id)
         return out.view(residual.shape)
 
     @staticmethod
@@ -420,8 +478,11 @@ class _Embedding(torch.autograd.Function):
         (idx32,) = ctx.saved_tensors
         wte = ctx.wte
         d = dout.contiguous()
-        if CONFIG.fuse_wgrad and wte.grad is not None and wte.grad.is_contiguous():
-            _C.embedding_bwd_(idx32, d, wte.grad)  # scatter-add into the shared (tied) gradient buffer
+        tgt = _grad_target(wte)
+        if tgt is not None:
+            # scatter-add into the shared (tied) gradient buffer.  The LM-head wgrad of the same backward pass has already
+            # written (overwrite mode) or accumulated into it, so this is always an accumulation.
+            _C.embedding_bwd_(idx32, d, tgt)
             return None, None
         dw = torch.zeros_like(wte)
         _C.embedding_bwd_(idx32, d, dw)

@@ -126,6 +126,7 @@ class FusedComm:
         self._ag_pending = [False] * self.nb
         self.epoch = 0
         self.stream = torch.cuda.Stream(device)
+        self.sm_count = torch.cuda.get_device_properties(device).multi_processor_count
         self.ready = [torch.cuda.Event() for _ in range(self.nb)]       # bucket b usable by compute
         self._ev = torch.cuda.Event()
         self._pending = [False] * self.nb
@@ -158,10 +159,14 @@ class FusedComm:
         self.epoch += 1
         self._pushed = [False] * self.nb
 
-    def bucket_update(self, b: int, *, master, m, v, lr, beta1, beta2, eps, wd, step, clip, grad_scale, side_sms: int = 0,
+    def bucket_update(self, b: int, *, master, m, v, lr, beta1, beta2, eps, wd, step, clip, grad_scale, background: bool = False,
                       reduced: bool = False, scale_mul: Optional[torch.Tensor] = None) -> None:
         """Bucket ``b``'s gradients are final on the current (compute) stream: reduce-scatter them
-        from every peer, apply AdamW to the owned shard and publish the new bf16 chunk."""
+        from every peer, apply AdamW to the owned shard and publish the new bf16 chunk.
+
+        ``background``: launch at most one small CTA per SM.  The tcgen05 GEMM / attention kernels cap their
+        register use so that such a CTA is co-resident with theirs: the update then runs *under* the rest of the
+        backward pass (on its spare memory bandwidth) instead of alternating with it."""
         e = self.epoch
         cur = torch.cuda.current_stream(self.device)
         self._ev.record(cur)
@@ -176,7 +181,7 @@ class FusedComm:
             mc_grad = self._grad.multicast_ptr if (self.nvls and not reduced) else 0
             mc_param = self._param.multicast_ptr if self.nvls else 0
             self._C.adamw_shard(master, m, v, self.flat_param, ptrs, self.grad_fp32, segs, n, tiles, lr, beta1, beta2, eps, wd, clip,
-                                grad_scale, step, 0, 0, side_sms, scale_mul.data_ptr() if scale_mul is not None else 0, mc_grad, mc_param)
+                                grad_scale, step, 0, 0, self.sm_count if background else 0, scale_mul.data_ptr() if scale_mul is not None else 0, mc_grad, mc_param)
             self._pushed[b] = bool(mc_param)
             if self.world > 1:
                 self._signal(FLAG_SHARD_READY, b, e)

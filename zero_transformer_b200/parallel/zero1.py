@@ -61,26 +61,21 @@ class Zero1Engine:
         decay_mask: Optional[Dict[str, bool]] = None,
         bucket_of=default_bucket_of,
         ag_gemm: bool = True,
-        comm_sms="auto",
+        comm_sms="auto",   # accepted for config compatibility; SM reservation was measured and dropped (round 1)
         clip_mode: str = "elementwise",
     ):
         self.model = model
         self.group = group
         self.ag_gemm = bool(ag_gemm)
         self.rank, self.world = _dist_info(group)
-        # SMs handed to the per-bucket reduce-scatter+AdamW kernels while the last micro-batch's backward
-        # runs (its persistent GEMMs shrink by as many).  A GEMM CTA needs a whole SM, so without a
-        # reservation the update kernel and the GEMMs alternate (each bucket's update runs between two
-        # GEMMs at full HBM bandwidth).  Measured on 1 GPU / 1.3B (bench.py, ms per step): 0 -> 263,
-        # 12 -> 268, 8 -> 289, 4 -> 369: one SM streams only ~45 GB/s, so a reservation large enough to keep
-        # up costs the GEMMs more than the alternation does.  "auto" therefore means 0; the knob is kept
-        # for larger worlds, where the per-rank update is 1/world of this.
-        env_sms = os.environ.get("ZTB_COMM_SMS")
-        if env_sms is not None:
-            comm_sms = int(env_sms)
-        elif comm_sms in ("auto", None):
-            comm_sms = 0
-        self.comm_sms = max(0, int(comm_sms)) & ~1
+        # How the per-bucket reduce-scatter+AdamW kernels share the GPU with the backward pass that is still running
+        # when they start.  A tcgen05 GEMM CTA owns its SM's shared memory and most of its registers, so a *wide* update
+        # kernel can only alternate with the GEMMs (measured round 1: 7.4 ms per step exposed on 1 GPU, and reserving
+        # whole SMs for it lost more than that).  "background" launches one 128-thread CTA per SM instead; the GEMM and
+        # attention kernels cap their registers so that this CTA is co-resident, and the update hides under backward.
+        # Buckets that become ready with less than `bg_min_blocks_left` blocks of backward still to run use the wide form.
+        self.update_mode = os.environ.get("ZTB_UPDATE_MODE", "background")
+        self.bg_min_blocks_left = int(os.environ.get("ZTB_BG_MIN_BLOCKS", "2"))
         self.lr_fn = lr_fn
         self.weight_decay = float(weight_decay)
         self.beta1, self.beta2 = float(betas[0]), float(betas[1])
@@ -183,7 +178,8 @@ class Zero1Engine:
             if self._two_phase:
                 self._fused.bucket_reduce(b)
             else:
-                self._fused.bucket_update(b, side_sms=self.comm_sms, **self._adam_kwargs())
+                bg = self.update_mode == "background" and i >= self.bg_min_blocks_left
+                self._fused.bucket_update(b, background=bg, **self._adam_kwargs())
             self._updated.add(b)
 
     def _on_block_forward_pre(self, i: int) -> None:
@@ -225,14 +221,9 @@ class Zero1Engine:
             self._fused.begin_step()
         self._in_engine_backward = True
         K.GRAD_MODE["accumulate"] = not self._overwrite_next
-        reserve = self.comm_sms if last else 0
-        if reserve:
-            K._C.set_sm_reserve(reserve)
         try:
             loss.backward()
         finally:
-            if reserve:
-                K._C.set_sm_reserve(0)
             K.GRAD_MODE["accumulate"] = True
             self._in_engine_backward = False
         self._overwrite_next = False
