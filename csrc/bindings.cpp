@@ -112,6 +112,17 @@ void embedding_bwd_(const at::Tensor& idx, const at::Tensor& dout, at::Tensor& d
                           (int)dwte.size(1), (int)dwte.size(0), stream()), "embedding_bwd");
 }
 
+// sorted_tok / order: the token ids in ascending order and the positions they came from (int32, from torch.sort)
+void embedding_bwd_sorted_(const at::Tensor& sorted_tok, const at::Tensor& order, const at::Tensor& dout, at::Tensor& dwte) {
+  need(sorted_tok.is_cuda() && sorted_tok.scalar_type() == at::kInt && sorted_tok.is_contiguous() && order.is_cuda() &&
+       order.scalar_type() == at::kInt && order.is_contiguous() && order.numel() == sorted_tok.numel(), "embedding_bwd_sorted: int32 index tensors");
+  need(is_bf16_cuda(dout) && dout.is_contiguous() && dwte.is_cuda() && dwte.is_contiguous() && dwte.size(1) % 8 == 0, "embedding_bwd_sorted: tensors");
+  need(dwte.scalar_type() == at::kBFloat16 || dwte.scalar_type() == at::kFloat, "embedding_bwd_sorted: grad dtype");
+  c10::cuda::CUDAGuard g(dout.device());
+  check(ztb_embedding_bwd_sorted(sorted_tok.data_ptr<int>(), order.data_ptr<int>(), dout.data_ptr(), dwte.data_ptr(), dwte.scalar_type() == at::kFloat,
+                                 (int)sorted_tok.numel(), (int)dwte.size(1), (int)dwte.size(0), stream()), "embedding_bwd_sorted");
+}
+
 at::Tensor gelu_bwd(const at::Tensor& dg, const at::Tensor& z) {
   need(is_bf16_cuda(dg) && is_bf16_cuda(z) && dg.is_contiguous() && z.is_contiguous() && dg.numel() % 8 == 0, "gelu_bwd: bf16 contiguous, numel % 8 == 0");
   c10::cuda::CUDAGuard g(z.device());
@@ -194,7 +205,7 @@ at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tens
 // Forward GEMM C = A * B^T with the ZeRO-1 all-gather of B's bucket fused into the kernel.
 at::Tensor gemm_ag(const at::Tensor& A, const at::Tensor& B, std::vector<int64_t> peer_ptrs, at::Tensor& local_flat, const at::Tensor& segs,
                    int64_t nseg, int64_t n_b_segs, int64_t total_tiles, int64_t shard_ready_ptr, int64_t epoch, at::Tensor& done,
-                   int64_t b_tiles_per_rank, int64_t rows_per_rank, int64_t world, int64_t rank) {
+                   int64_t b_tiles_per_rank, int64_t rows_per_rank, int64_t world, int64_t rank, bool two_cta) {
   need(is_bf16_cuda(A) && is_bf16_cuda(B) && A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "gemm_ag: A, B bf16 2-D");
   need(A.size(1) == B.size(1), "gemm_ag: K mismatch");
   need(done.is_cuda() && done.numel() >= 8 && done.element_size() == 4, "gemm_ag: done must be an 8-element 32-bit CUDA tensor");
@@ -213,7 +224,7 @@ at::Tensor gemm_ag(const at::Tensor& A, const at::Tensor& B, std::vector<int64_t
   a.M = A.size(0); a.K = A.size(1); a.N = B.size(0);
   a.lda = A.stride(0); a.ldb = B.stride(0); a.ldc = C.stride(0);
   a.ag = &ag;
-  a.direct_store = -1; a.raster_n = -1;
+  a.direct_store = -1; a.raster_n = -1; a.two_cta = two_cta;
   check(ztb_gemm(&a, num_sms(), stream()), "gemm_ag");
   return C;
 }
@@ -325,6 +336,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dropout_add", &dropout_add);
   m.def("embedding_fwd", &embedding_fwd);
   m.def("embedding_bwd_", &embedding_bwd_);
+  m.def("embedding_bwd_sorted_", &embedding_bwd_sorted_);
   m.def("gelu_fwd", &gelu_fwd);
   m.def("gelu_bwd", &gelu_bwd);
   m.def("ce_fwd", &ce_fwd);
@@ -333,7 +345,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("aux_out") = py::none(), py::arg("p") = 0.0, py::arg("rng") = py::none(), py::arg("op_id") = 0,
         py::arg("accumulate") = false, py::arg("a_mn") = false, py::arg("b_mn") = false, py::arg("two_cta") = false, py::arg("no_split") = false,
         py::arg("direct_store") = -1, py::arg("raster_n") = -1);
-  m.def("gemm_ag", &gemm_ag);
+  m.def("gemm_ag", &gemm_ag, py::arg("A"), py::arg("B"), py::arg("peer_ptrs"), py::arg("local_flat"), py::arg("segs"), py::arg("nseg"),
+        py::arg("n_b_segs"), py::arg("total_tiles"), py::arg("shard_ready_ptr"), py::arg("epoch"), py::arg("done"), py::arg("b_tiles_per_rank"),
+        py::arg("rows_per_rank"), py::arg("world"), py::arg("rank"), py::arg("two_cta") = false);
   m.def("adamw_shard", &adamw_shard, py::arg("master"), py::arg("m"), py::arg("v"), py::arg("flat_param"), py::arg("grad_ptrs"),
         py::arg("grad_is_fp32"), py::arg("segs"), py::arg("nseg"), py::arg("total_tiles"), py::arg("lr"), py::arg("beta1"), py::arg("beta2"),
         py::arg("eps"), py::arg("wd"), py::arg("clip"), py::arg("grad_scale"), py::arg("step"), py::arg("wait_flags_ptr") = 0,

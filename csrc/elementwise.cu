@@ -297,6 +297,62 @@ __global__ void __launch_bounds__(128) embedding_bwd_kernel(const int* __restric
   }
 }
 
+// Deterministic scatter-add for real corpora: the token ids are sorted first (host side: one torch.sort of M ints), every
+// run of equal ids is cut into chunks of kEmbChunk rows, one warp sums a chunk in fp32 and adds it to the gradient row once.
+// A token that occurs once per chunk-run (the common case) is a plain read-modify-write; only tokens with more than
+// kEmbChunk occurrences meet through atomics, with one rounding per 32 occurrences instead of one per occurrence.
+// (The plain kernel above rounds to bf16 on every occurrence: a frequent token's later increments vanish once the running
+// sum is ~256x the addend.)
+constexpr int kEmbChunk = 32;
+template <typename G>
+__global__ void __launch_bounds__(128) embedding_bwd_sorted_kernel(const int* __restrict__ sorted_tok, const int* __restrict__ order,
+                                                                   const bf16* __restrict__ dout, G* __restrict__ dwte, int M, int D, int V) {
+  const int p = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= M) return;
+  const int tok = sorted_tok[p];
+  if (tok < 0 || tok >= V) return;
+  int lo = 0, hi = p;                       // first position holding `tok`
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (sorted_tok[mid] < tok) lo = mid + 1; else hi = mid;
+  }
+  if ((p - lo) % kEmbChunk != 0) return;    // not a chunk start
+  int end = p + 1;
+  while (end < M && end < p + kEmbChunk && sorted_tok[end] == tok) ++end;
+  const bool shared_row = p != lo || (end < M && sorted_tok[end] == tok);   // another chunk adds into the same row
+  G* grow = dwte + (size_t)tok * D;
+  for (int c = lane; c < D / 8; c += 32) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int q = p; q < end; ++q) {
+      uint4 u = ld_nc_v4(dout + (size_t)order[q] * D + c * 8);
+      float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += cc.x; acc[5] += cc.y; acc[6] += d.x; acc[7] += d.y;
+    }
+    if constexpr (sizeof(G) == 2) {
+      bf16* g = reinterpret_cast<bf16*>(grow) + c * 8;
+      if (shared_row) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(reinterpret_cast<bf162*>(g) + k, __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]));
+      } else {
+        uint4 o = ld_v4(g);
+        float2 a = unpack_bf16(o.x), b = unpack_bf16(o.y), cc = unpack_bf16(o.z), d = unpack_bf16(o.w);
+        st_v4(g, make_uint4(pack_bf16(a.x + acc[0], a.y + acc[1]), pack_bf16(b.x + acc[2], b.y + acc[3]),
+                            pack_bf16(cc.x + acc[4], cc.y + acc[5]), pack_bf16(d.x + acc[6], d.y + acc[7])));
+      }
+    } else {
+      float* g = reinterpret_cast<float*>(grow) + c * 8;
+      if (shared_row) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(g + k, acc[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] += acc[k];
+      }
+    }
+  }
+}
+
 // ============================================================== GELU backward
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const bf16* __restrict__ dg, const bf16* __restrict__ z,
                                                        bf16* __restrict__ dz, size_t n8) {
@@ -477,6 +533,16 @@ int ztb_embedding_bwd(const int* idx, const void* dout, void* dwte, int grad_is_
     embedding_bwd_kernel<float><<<(M + 3) / 4, 128, 0, st>>>(idx, (const bf16*)dout, (float*)dwte, M, D, V);
   else
     embedding_bwd_kernel<bf16><<<(M + 3) / 4, 128, 0, st>>>(idx, (const bf16*)dout, (bf16*)dwte, M, D, V);
+  ZTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int ztb_embedding_bwd_sorted(const int* sorted_tok, const int* order, const void* dout, void* dwte, int grad_is_fp32, int M, int D, int V,
+                             cudaStream_t st) {
+  if (grad_is_fp32)
+    embedding_bwd_sorted_kernel<float><<<(M + 3) / 4, 128, 0, st>>>(sorted_tok, order, (const bf16*)dout, (float*)dwte, M, D, V);
+  else
+    embedding_bwd_sorted_kernel<bf16><<<(M + 3) / 4, 128, 0, st>>>(sorted_tok, order, (const bf16*)dout, (bf16*)dwte, M, D, V);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

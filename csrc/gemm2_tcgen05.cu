@@ -54,7 +54,10 @@ struct GemmParams {
   // 32-column half): bit 0 = the auxiliary output (pre-activation Z), bit 1 = a non-accumulating bf16 C.
   int direct;
   bf16* c_raw; bf16* aux_raw; long long ldc_raw, ld_aux_raw;
-  int raster_n;   // walk tiles in groups of GROUP_M column blocks (vocabulary-sized N: the A panel stays in L2)
+  int raster_n;   // 1: walk tiles in groups of GROUP_M column blocks (vocabulary-sized N: the A panel stays in L2)
+                  // 2: all row blocks of one column block, column blocks rotated by nb_shift (all-gather variant: the
+                  //    column blocks this rank owns come first)
+  int nb_shift;
 };
 
 struct Unit { int tile, kb0, kb1, partial, part; };
@@ -74,6 +77,12 @@ ZTB_DEVINL bool get_unit(int u, const GemmParams& p, int kblocks, Unit& w) {
 }
 
 ZTB_DEVINL void decode_tile(int t, const GemmParams& p, int& mb, int& nb) {
+  if (p.raster_n == 2) {
+    mb = t % p.tiles_m;
+    nb = t / p.tiles_m + p.nb_shift;
+    if (nb >= p.tiles_n) nb -= p.tiles_n;
+    return;
+  }
   if (p.raster_n) {
     int per_group = GROUP_M * p.tiles_m;
     int g = t / per_group, r = t % per_group;
@@ -130,22 +139,74 @@ ZTB_DEVINL void mbar_arrive_cta0(uint64_t* bar) {  // arrive on CTA 0's copy of 
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-template <bool A_MN, bool B_MN, int EPI>
+// ---------------------------------------------------------------------------------------------------------------
+// All-gather fused into the GEMM (ZeRO-1 parameter all-gather + the first GEMM that consumes the gathered weight;
+// SURVEY 2.4-B X3, reference main_zero.py:452-456,500 where XLA inserts an fp32 all-gather in front of the step).
+// B is a weight whose row chunks are owned by different ranks.  One spare warp of EVERY CTA is a copy engine driver: an
+// elected thread streams the remote chunks of the weight's whole ZeRO-1 bucket from the owners' symmetric buffers into
+// the local flat parameter buffer with bulk async copies (peer global -> shared ring -> local global; the TMA unit
+// moves the bytes, no register round trip), B's own chunks first.  Meanwhile the tensor cores work through the N blocks
+// this rank owns; the TMA producers of the other N blocks acquire a per-owner "B chunk landed" counter first.
+constexpr int AG_TILE_ELEMS = 4096;                 // 8 KB per bulk copy
+constexpr int AG_TILE_BYTES = AG_TILE_ELEMS * 2;
+constexpr int AG_SLOTS = 4;                         // copies in flight per CTA: 148 x 32 KB covers NVLink bandwidth x latency
+constexpr int STAGES_AG = 4;                        // the AG variant gives one operand stage (32 KB) to the gather ring
+
+struct AgParams {
+  const void* peer[8];          // flat bf16 parameter buffer of every rank (peer-mapped), index = rank
+  bf16* local;                  // this rank's flat parameter buffer
+  const ZtbSegment* segs;       // pull list: flat_off, len, decay = source rank, tile_begin (AG_TILE_ELEMS units); B's segments first
+  int nseg;
+  int n_b_segs;                 // the first n_b_segs segments are B's chunks (one per remote rank)
+  long long total_tiles;
+  const int* shard_ready;       // my flag row: [rank] >= epoch once that rank's chunk is final
+  int epoch;
+  unsigned int* done;           // [8] per-owner count of landed B tiles (zeroed before launch)
+  unsigned int b_tiles_per_rank;
+  int rows_per_rank;            // B rows owned by each rank
+  int world, rank;
+};
+
+ZTB_DEVINL int ld_acquire_sys_s32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+ZTB_DEVINL unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// 1-D bulk async copies (the TMA unit without a tensor map): global -> shared with mbarrier completion, shared -> global
+ZTB_DEVINL void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+ZTB_DEVINL void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+
+template <bool A_MN, bool B_MN, int EPI, bool AG>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
-                     const GemmParams p) {
+                     const GemmParams p, const __grid_constant__ AgParams ag) {
+  constexpr int NST = AG ? STAGES_AG : STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
-  uint8_t* smB = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* smC = smem + STAGES * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smC + CSTAGE_BYTES);
-  uint64_t* full = bars;                     // [STAGES]  leader's copy collects both CTAs' TMA bytes
-  uint64_t* empty = bars + STAGES;           // [STAGES]  multicast commit -> both CTAs
+  uint8_t* smB = smem + NST * A_STAGE_BYTES;
+  uint8_t* smC = smem + NST * STAGE_BYTES;
+  uint8_t* smG = smC + CSTAGE_BYTES;         // AG only: AG_SLOTS x 8 KB gather ring (the space of the fifth operand stage)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + CSTAGE_BYTES);
+  uint64_t* full = bars;                     // [NST]  leader's copy collects both CTAs' TMA bytes
+  uint64_t* empty = bars + STAGES;           // [NST]  multicast commit -> both CTAs
   uint64_t* tfull = bars + 2 * STAGES;       // [2]       multicast commit -> both CTAs
   uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]       leader's copy: 8 epilogue warps (both CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* gfull = bars + 2 * STAGES + 5;   // [AG_SLOTS] gather ring: bulk load landed
+  static_assert(AG_SLOTS * AG_TILE_BYTES == STAGE_BYTES, "the gather ring takes exactly one operand stage");
+  static_assert((2 * STAGES + 5 + AG_SLOTS) * 8 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -158,8 +219,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (p.has_aux_out) prefetch_tmap(&tmAux);
   }
   if (warp == 9 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * EPI_WARPS); }
+    if constexpr (AG) { for (int i = 0; i < AG_SLOTS; ++i) mbar_init(&gfull[i], 1); }
     fence_barrier_init();
   }
   if (warp == 10) {
@@ -182,6 +244,16 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         int mb, nb; decode_tile(w.tile, p, mb, nb);
         const int m0 = mb * TILE_M + cta_rank * BM;        // this CTA's A rows
         const int nrow0 = nb * BN + cta_rank * 128;        // this CTA's B rows
+        if constexpr (AG) {
+          // rows [nrow0, nrow0 + 128) of B: every owner other than this rank must have landed in the local buffer
+          int r0 = nrow0 / ag.rows_per_rank, r1 = (nrow0 + 127) / ag.rows_per_rank;
+          if (r0 >= ag.world) r0 = ag.world - 1;
+          if (r1 >= ag.world) r1 = ag.world - 1;
+          for (int o = r0; o <= r1; ++o)
+            if (o != ag.rank)
+              while ((unsigned)ld_acquire_gpu(reinterpret_cast<const int*>(ag.done + o)) < ag.b_tiles_per_rank) __nanosleep(64);
+          asm volatile("fence.proxy.async.global;" ::: "memory");   // the gathered rows were written by bulk copies of other CTAs
+        }
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (leader) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
@@ -199,7 +271,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
             for (int j = 0; j < 2; ++j) tma_load_2d_2sm(b + j * 8192, &tmB, &full[stage], nrow0 + j * 64, kb * BK);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -229,9 +301,80 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
           umma_commit_2sm(&empty[stage]);
           if (kb == w.kb1 - 1) umma_commit_2sm(&tfull[acc]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (AG && warp == 11) {
+    // ===================================================== all-gather driver (one thread per CTA, bulk copies over NVLink)
+    if constexpr (AG) {
+      if (lane == 0) {
+        unsigned seen = 1u << ag.rank;
+        // Ring of AG_SLOTS 8 KB slots.  Copy i uses slot i % AG_SLOTS: bulk-load peer -> slot (mbarrier), bulk-store
+        // slot -> local buffer (bulk group).  Loads run AG_SLOTS - 1 ahead of the stores; a slot is reloaded once the
+        // store that read it has finished reading shared memory; a B tile is published to the TMA producers once its
+        // store has completed (bulk groups complete in order, so wait_group<k> tells how far completion got).
+        long long issued = 0, stored = 0, published = 0;
+        const long long first = blockIdx.x, step = gridDim.x;
+        const long long mine = ag.total_tiles > first ? (ag.total_tiles - first + step - 1) / step : 0;
+        auto tile_info = [&](long long i, const bf16*& src, bf16*& dst, uint32_t& bytes, int& owner, bool& is_b) {
+          const long long t = first + i * step;
+          int lo = 0, hi = ag.nseg - 1;
+          while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (ag.segs[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
+          }
+          const ZtbSegment sg = ag.segs[lo];
+          const long long e0 = (t - sg.tile_begin) * AG_TILE_ELEMS;
+          const long long left = sg.len - e0;
+          bytes = (uint32_t)((left < AG_TILE_ELEMS ? left : AG_TILE_ELEMS) * 2);
+          owner = sg.decay; is_b = lo < ag.n_b_segs;
+          src = reinterpret_cast<const bf16*>(ag.peer[owner]) + sg.flat_off + e0;
+          dst = ag.local + sg.flat_off + e0;
+        };
+        auto issue_load = [&](long long i) {
+          const bf16* src; bf16* dst; uint32_t bytes; int owner; bool is_b;
+          tile_info(i, src, dst, bytes, owner, is_b);
+          if (!((seen >> owner) & 1u)) {   // the owner has published this step's chunk?
+            const unsigned long long t0 = globaltimer_ns();
+            while (ld_acquire_sys_s32(ag.shard_ready + owner) < ag.epoch) {
+              __nanosleep(64);
+              if (globaltimer_ns() - t0 > 120ull * 1000000000ull) __trap();   // owner never published its shard: fail loudly
+            }
+            seen |= 1u << owner;
+          }
+          const int slot = (int)(i % AG_SLOTS);
+          mbar_expect_tx(&gfull[slot], bytes);
+          bulk_load_1d(smG + slot * AG_TILE_BYTES, src, bytes, &gfull[slot]);
+        };
+        auto publish = [&](long long i) {   // store i has completed
+          const bf16* src; bf16* dst; uint32_t bytes; int owner; bool is_b;
+          tile_info(i, src, dst, bytes, owner, is_b);
+          if (is_b) {
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ag.done + owner) : "memory");
+          }
+        };
+        while (issued < mine && issued < AG_SLOTS - 1) issue_load(issued++);
+        for (; stored < mine; ++stored) {
+          const int slot = (int)(stored % AG_SLOTS);
+          mbar_wait(&gfull[slot], (uint32_t)((stored / AG_SLOTS) & 1));
+          const bf16* src; bf16* dst; uint32_t bytes; int owner; bool is_b;
+          tile_info(stored, src, dst, bytes, owner, is_b);
+          bulk_store_1d(dst, smG + slot * AG_TILE_BYTES, bytes);
+          tma_commit_group();
+          if (issued < mine) {
+            // copy `issued` reuses the slot that store `stored - 1` read: only the store just issued may still be reading
+            tma_wait_group_read<1>();
+            issue_load(issued++);
+          }
+          // stores complete in order: all but the newest AG_SLOTS - 1 have finished
+          tma_wait_group<AG_SLOTS - 1>();
+          for (; published + (AG_SLOTS - 1) <= stored; ++published) publish(published);
+        }
+        tma_wait_group<0>();
+        for (; published < mine; ++published) publish(published);
       }
     }
   } else if (warp < 8) {
@@ -431,16 +574,18 @@ using namespace ztb;
 int ztb_make_tmap_2d(CUtensorMap* tm, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
                      int box_cols, int box_rows);
 
-template <bool A_MN, bool B_MN, int EPI>
+template <bool A_MN, bool B_MN, int EPI, bool AG = false>
 static int launch2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& x, const g2::GemmParams& p,
-                   int grid, cudaStream_t st) {
-  auto kern = g2::gemm2_tcgen05_kernel<A_MN, B_MN, EPI>;
+                   int grid, cudaStream_t st, const g2::AgParams* agp = nullptr) {
+  auto kern = g2::gemm2_tcgen05_kernel<A_MN, B_MN, EPI, AG>;
   static bool configured = false;
   if (!configured) {
     ZTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g2::GEMM_SMEM));
     configured = true;
   }
-  kern<<<grid, g2::GEMM_THREADS, g2::GEMM_SMEM, st>>>(a, b, c, x, p);  // cluster dims are compile-time (2,1,1)
+  g2::AgParams ag{};
+  if (agp) ag = *agp;
+  kern<<<grid, g2::GEMM_THREADS, g2::GEMM_SMEM, st>>>(a, b, c, x, p, ag);  // cluster dims are compile-time (2,1,1)
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -478,6 +623,10 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
   const bool supported = g->epilogue == ZTB_EPI_NONE || (major == 0 && (g->epilogue == ZTB_EPI_GELU || g->epilogue == ZTB_EPI_DROPOUT_ADD)) ||
                          (major == 1 && g->epilogue == ZTB_EPI_GELU_BWD);
   if (!supported) return -2;
+  if (g->ag != nullptr && (major != 0 || g->epilogue != ZTB_EPI_NONE || g->accumulate || g->c_is_fp32)) {
+    ztb_set_error("ztb_gemm_2cta", "all-gather fusion is implemented for the plain K-major forward GEMM", __FILE__, __LINE__);
+    return -1;
+  }
   if ((g->lda % 8) || (g->ldb % 8) || (g->ldc % (g->c_is_fp32 ? 4 : 8)) || (g->K % 8) || (g->N % 8)) {
     ztb_set_error("ztb_gemm_2cta", "leading dimensions / K / N must be multiples of 8 elements", __FILE__, __LINE__);
     return -1;
@@ -524,6 +673,22 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
   // ceil(tail * split / pairs) / split of a tile time instead of a whole one.
   const int kblocks = (g->K + BK - 1) / BK;
   p.full_tiles = p.num_tiles / pairs * pairs; p.tail = p.num_tiles - p.full_tiles; p.split = 1;
+  p.nb_shift = 0;
+  if (g->ag != nullptr) {
+    // all-gather variant: every CTA takes part in the gather (even with fewer tiles than CTA pairs), the column blocks
+    // this rank owns are computed first, whole tiles only
+    const ZtbAgArgs* a = g->ag;
+    AgParams ag{};
+    for (int i = 0; i < 8; ++i) ag.peer[i] = i < a->world ? a->peer[i] : nullptr;
+    ag.local = (bf16*)a->local; ag.segs = a->segs; ag.nseg = a->nseg; ag.n_b_segs = a->n_b_segs; ag.total_tiles = a->total_tiles;
+    ag.shard_ready = a->shard_ready; ag.epoch = a->epoch; ag.done = a->done; ag.b_tiles_per_rank = a->b_tiles_per_rank;
+    ag.rows_per_rank = a->rows_per_rank; ag.world = a->world; ag.rank = a->rank;
+    ZTB_CUDA_CHECK(cudaMemsetAsync(a->done, 0, 8 * sizeof(unsigned), st));
+    p.raster_n = 2;
+    p.nb_shift = ((a->rank * a->rows_per_rank) / BN) % p.tiles_n;
+    p.full_tiles = p.num_tiles; p.tail = 0; p.split = 1; p.chain = nullptr; p.direct = 0;
+    return launch2<false, false, ZTB_EPI_NONE, true>(ta, tb, tc, tx, p, pairs * 2, st, &ag);
+  }
   if (p.tail > 0 && g->epilogue == ZTB_EPI_NONE && !g->no_split) {
     float best = 1.f;
     for (int sp = 2; sp <= 8 && kblocks / sp >= 16; ++sp) {

@@ -438,7 +438,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
 
 int ztb_gemm(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
   if (g->M <= 0 || g->N <= 0 || g->K <= 0) return 0;
-  if (g->two_cta && !g->ag) {
+  if (g->two_cta) {
     const int rc2 = ztb_gemm_2cta(g, sms, st);
     if (rc2 != -2) return rc2;   // -2: that (operand major, epilogue) pair only exists in this general kernel
   }

@@ -24,6 +24,8 @@ int ztb_dropout_add(const void* y, const void* res, void* out, size_t n, float p
                     int sms, cudaStream_t st);
 int ztb_embedding_fwd(const int* idx, const void* wte, void* out, int M, int D, int V, cudaStream_t st);
 int ztb_embedding_bwd(const int* idx, const void* dout, void* dwte, int grad_is_fp32, int M, int D, int V, cudaStream_t st);
+int ztb_embedding_bwd_sorted(const int* sorted_tok, const int* order, const void* dout, void* dwte, int grad_is_fp32, int M, int D, int V,
+                             cudaStream_t st);
 int ztb_gelu_bwd(const void* dg, const void* z, void* dz, size_t n, int sms, cudaStream_t st);
 int ztb_gelu_fwd(const void* z, void* g, size_t n, int sms, cudaStream_t st);
 int ztb_ce_fwd(const void* logits, const int* labels, float* lse, float* nll, int M, int V, size_t ld, cudaStream_t st);

@@ -64,7 +64,9 @@ def test_warm_start_with_depth_extension(tmp_path):
     ckpt.save_checkpoint(e, str(tmp_path), 2)
     m4, e4 = _mk(N=4, seed=3)
     ckpt.warm_start(e4, str(tmp_path), extend_depth=True)
-    assert e4.step_count == 0  # step is not adopted (reference main_zero.py:268-289)
+    # the optimizer counter (Adam bias correction + LR schedule) travels with the moments, as in the reference
+    # (ScaleByAdamState.count / ScaleByScheduleState.count, main_zero.py:105-139); the *training* step stays with the Trainer
+    assert e4.step_count == 2
     src = dict(m.named_parameters())
     dst = dict(m4.named_parameters())
     for j in range(4):

@@ -8,7 +8,14 @@ re-chunking of ``max_context`` rows into ``train_context`` rows -- plus what the
 benchmark protocol needs: a synthetic random-token source and a pinned-memory
 prefetcher that overlaps the host->device copy with the previous step.
 
-Shard formats (local files; the reference streamed WebDataset tars from GCS):
+Shard locations: plain paths and ``file://`` are opened directly; any other ``scheme://`` URL goes through a
+pluggable *opener* (``register_opener``).  Built in: ``http(s)://`` (urllib), ``gs://`` (``gcloud storage cat`` /
+``gsutil cat`` subprocess pipe, the reference's GCS buckets, ``main_zero.py:368-421``) and ``pipe:<command>``
+(WebDataset's convention).  Index files may therefore be copied over unchanged from the reference; a scheme whose
+transport is unavailable (no network, no gcloud) fails when the shard is *opened*, with the URL in the message, and the
+loader skips that shard like any other unreadable one.
+
+Shard formats:
   ``*.npy``  2-D integer array ``(n_samples, >=max_context)``
   ``*.bin``  raw little-endian uint16 token stream, cut into ``max_context`` rows
   ``*.tar``  members ending in ``.npy`` or ``.pth`` (e.g. ``<key>.input_id.pth``,
@@ -22,15 +29,71 @@ import queue
 import random
 import tarfile
 import threading
-from typing import Iterable, Iterator, List, Optional, Sequence
+from typing import BinaryIO, Callable, Dict, Iterable, Iterator, List, Optional, Sequence
 
 import numpy as np
 import torch
 
 
+# scheme -> callable(url) -> binary file object.  Looked up when a shard is opened, never when the index is read.
+_OPENERS: Dict[str, Callable[[str], BinaryIO]] = {}
+
+
+def register_opener(scheme: str, fn: Callable[[str], BinaryIO]) -> None:
+    """Plug in a transport for ``<scheme>://...`` shard URLs (``fn(url)`` returns a readable binary stream)."""
+    _OPENERS[scheme.lower()] = fn
+
+
+def _open_http(url: str) -> BinaryIO:
+    import urllib.request
+
+    return urllib.request.urlopen(url, timeout=60)  # noqa: S310 - user-supplied shard list
+
+
+def _open_pipe(cmd: str) -> BinaryIO:
+    import subprocess
+
+    proc = subprocess.Popen(cmd, shell=True, stdout=subprocess.PIPE, bufsize=1 << 20)  # noqa: S602 - WebDataset "pipe:" convention
+    return proc.stdout
+
+
+def _open_gs(url: str) -> BinaryIO:
+    import shutil
+
+    for tool in (["gcloud", "storage", "cat"], ["gsutil", "cat"]):
+        if shutil.which(tool[0]):
+            return _open_pipe(" ".join(tool) + " '" + url.replace("'", "") + "'")
+    raise OSError(f"cannot open {url}: neither gcloud nor gsutil is installed (register_opener('gs', ...) to plug in another client)")
+
+
+register_opener("http", _open_http)
+register_opener("https", _open_http)
+register_opener("gs", _open_gs)
+
+
+def _scheme(loc: str) -> str:
+    if loc.startswith("pipe:"):
+        return "pipe"
+    return loc.split("://", 1)[0].lower() if "://" in loc else ""
+
+
+def open_shard(loc: str) -> BinaryIO:
+    """Binary stream of a shard location (local path, ``file://``, ``pipe:cmd`` or a registered ``scheme://``)."""
+    sch = _scheme(loc)
+    if sch == "":
+        return open(loc, "rb")
+    if sch == "file":
+        return open(loc[len("file://"):], "rb")
+    if sch == "pipe":
+        return _open_pipe(loc[len("pipe:"):])
+    if sch not in _OPENERS:
+        raise OSError(f"no opener registered for '{sch}://' shard URLs ({loc})")
+    return _OPENERS[sch](loc)
+
+
 def read_index(path: str) -> List[str]:
     """One shard path/URL per line; blank lines and ``#`` comments ignored.
-    Relative paths resolve against the index file's directory."""
+    Relative paths resolve against the index file's directory; URLs are kept verbatim."""
     base = os.path.dirname(os.path.abspath(path))
     out = []
     with open(path, "r") as f:
@@ -38,12 +101,12 @@ def read_index(path: str) -> List[str]:
             s = line.strip()
             if not s or s.startswith("#"):
                 continue
-            if "://" in s:
-                if s.startswith("file://"):
-                    s = s[len("file://"):]
-                else:
-                    raise ValueError(f"{path}: remote shard '{s}' -- only local paths are supported (no network)")
-            out.append(s if os.path.isabs(s) else os.path.join(base, s))
+            if _scheme(s) == "file":
+                s = s[len("file://"):]
+            if _scheme(s):
+                out.append(s)
+            else:
+                out.append(s if os.path.isabs(s) else os.path.join(base, s))
     return out
 
 
@@ -55,9 +118,26 @@ def split_by_rank(shards: Sequence[str], rank: int, world: int) -> List[str]:
     return list(shards[rank::world])
 
 
+def _suffix(loc: str) -> str:
+    return os.path.splitext(loc.split("?", 1)[0].rstrip("'\" "))[1].lower()
+
+
 def _iter_shard(path: str, max_context: int) -> Iterator[np.ndarray]:
+    remote = _scheme(path) != ""
     try:
-        if path.endswith(".npy"):
+        if remote and _suffix(path) in (".npy", ".bin"):
+            # array shards need random access: spool the stream to memory first
+            raw = open_shard(path).read()
+            if _suffix(path) == ".npy":
+                arr = np.load(io.BytesIO(raw))
+            else:
+                arr = np.frombuffer(raw, dtype=np.uint16)
+            if arr.ndim == 1:
+                arr = arr[: (arr.shape[0] // max_context) * max_context].reshape(-1, max_context)
+            for row in arr:
+                if row.shape[0] >= max_context:
+                    yield np.asarray(row[:max_context], dtype=np.int32)
+        elif path.endswith(".npy"):
             arr = np.load(path, mmap_mode="r")
             if arr.ndim == 1:
                 arr = arr[: (arr.shape[0] // max_context) * max_context].reshape(-1, max_context)
@@ -69,8 +149,9 @@ def _iter_shard(path: str, max_context: int) -> Iterator[np.ndarray]:
             n = arr.shape[0] // max_context
             for i in range(n):
                 yield np.asarray(arr[i * max_context:(i + 1) * max_context], dtype=np.int32)
-        elif path.endswith(".tar"):
-            with tarfile.open(path, "r") as tf:
+        elif _suffix(path) == ".tar":
+            # "r|" = sequential stream: works for local files and for sockets / subprocess pipes alike
+            with tarfile.open(fileobj=open_shard(path), mode="r|") as tf:
                 for m in tf:
                     if not m.isfile():
                         continue
@@ -171,6 +252,16 @@ def batch_iterator(samples: Iterable[np.ndarray], batch_rows: int, drop_last: bo
         yield numpy_collate(buf)
 
 
+def skip_batches(batches: Iterable[np.ndarray], n: int) -> Iterator[np.ndarray]:
+    """Drop the first ``n`` batches: the resume fast-forward of the reference loop (``if i < iterator_resume_step: continue``,
+    ``main_zero.py:437,470-471``), done on the host before anything is copied to the device."""
+    it = iter(batches)
+    for _ in range(max(int(n), 0)):
+        if next(it, None) is None:
+            return
+    yield from it
+
+
 def rechunk(batch: torch.Tensor, train_context: int) -> torch.Tensor:
     """``(B, max_context)`` -> ``(B * max_context/train_context, train_context)``
     (reference ``main_zero.py:425-428,477-478``)."""
@@ -202,6 +293,17 @@ class DevicePrefetcher:
         self.t = threading.Thread(target=self._run, args=(iter(batches),), daemon=True)
         self.t.start()
 
+    def _put(self, item) -> bool:
+        """Blocking put that gives up when the consumer closed the prefetcher (so the thread, the dataset generator and
+        its shuffle buffer are released instead of staying parked in ``q.put`` forever)."""
+        while not self._stop:
+            try:
+                self.q.put(item, timeout=0.2)
+                return True
+            except queue.Full:
+                continue
+        return False
+
     def _run(self, it):
         try:
             for b in it:
@@ -214,13 +316,21 @@ class DevicePrefetcher:
                         dev = host.to(self.device, non_blocking=True)
                         ev = torch.cuda.Event()
                         ev.record(self.stream)
-                    self.q.put((dev, ev, host))
-                else:
-                    self.q.put((host, None, host))
+                    if not self._put((dev, ev, host)):
+                        return
+                elif not self._put((host, None, host)):
+                    return
         except Exception as e:  # surface loader errors in the consumer
-            self.q.put(e)
+            self._put(e)
             return
-        self.q.put(None)
+        finally:
+            close = getattr(it, "close", None)   # generator: run its cleanup now, not at garbage collection
+            if close is not None:
+                try:
+                    close()
+                except Exception:
+                    pass
+        self._put(None)
 
     def __iter__(self):
         return self
@@ -245,3 +355,12 @@ class DevicePrefetcher:
                 self.q.get_nowait()
         except queue.Empty:
             pass
+        if self.t.is_alive() and threading.current_thread() is not self.t:
+            self.t.join(timeout=5.0)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False

@@ -77,6 +77,7 @@ class _Config:
     fuse_wgrad = os.environ.get("ZTB_FUSE_WGRAD", "1") == "1"    # accumulate dW into param.grad in the epilogue
     gemm_2cta = os.environ.get("ZTB_GEMM_2CTA", "1") == "1"      # cta_group::2 256x256 kernel for the big GEMMs
     attn_impl = os.environ.get("ZTB_ATTN", "auto")                # auto | tc (own kernel) | flash (flash_attn library) | ref
+    embedding_bwd_sorted = os.environ.get("ZTB_EMB_BWD_SORTED", "1") == "1"  # fp32 per-token sums, one add per gradient row
     fold_dropout_bwd = os.environ.get("ZTB_FOLD_DROPOUT_BWD", "1") == "1"  # LayerNorm-backward emits the masked gradient
 
 
@@ -479,14 +480,16 @@ class _Embedding(torch.autograd.Function):
         wte = ctx.wte
         d = dout.contiguous()
         tgt = _grad_target(wte)
-        if tgt is not None:
-            # scatter-add into the shared (tied) gradient buffer.  The LM-head wgrad of the same backward pass has already
-            # written (overwrite mode) or accumulated into it, so this is always an accumulation.
-            _C.embedding_bwd_(idx32, d, tgt)
-            return None, None
-        dw = torch.zeros_like(wte)
-        _C.embedding_bwd_(idx32, d, dw)
-        return None, dw
+        dw = tgt if tgt is not None else torch.zeros_like(wte)
+        # Scatter-add into the shared (tied) gradient buffer.  The LM-head wgrad of the same backward pass has already
+        # written (overwrite mode) or accumulated into it, so this is always an accumulation.  Default: sort the ids, sum
+        # each token's occurrences in fp32 and add once per row (deterministic, no per-occurrence bf16 rounding).
+        if CONFIG.embedding_bwd_sorted:
+            stok, order = torch.sort(idx32.view(-1).to(torch.int64), stable=True)
+            _C.embedding_bwd_sorted_(stok.to(torch.int32), order.to(torch.int32), d.view(-1, d.shape[-1]), dw)
+        else:
+            _C.embedding_bwd_(idx32, d, dw)
+        return None, (None if tgt is not None else dw)
 
 
 def embedding(idx, wte):

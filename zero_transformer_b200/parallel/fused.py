@@ -26,7 +26,8 @@ import torch
 import torch.distributed as dist
 
 ADAM_TILE = 1024  # elements per CTA tile; must match kAdamTile in csrc/optim.cu
-COPY_TILE = 8192  # must match kCopyTile in csrc/comm.cu
+COPY_TILE = 8192  # must match kCopyTile in csrc/comm.cu (and AG_TILE of the 1-CTA all-gather GEMM)
+AG2_TILE = 4096   # must match AG_TILE_ELEMS in csrc/gemm2_tcgen05.cu (bulk-copy gather of the CTA-pair all-gather GEMM)
 RS_TILE = 2048    # elements per CTA tile of csrc/comm.cu reduce_scatter_kernel
 FLAG_GRAD_READY, FLAG_SHARD_READY = 0, 1
 MAX_RANKS = 8
@@ -123,6 +124,9 @@ class FusedComm:
         # all-gather fused into the bucket's first GEMM: pull list with that weight's chunks first
         self.ag_lists = {}
         self.ag_done = torch.zeros(8, dtype=torch.int32, device=device)
+        # CTA-pair (cta_group::2) all-gather GEMM with a bulk-copy (TMA) gather ring; 0 = the 1-CTA kernel whose gather
+        # warps move the data through registers (round 1)
+        self.ag_two_cta = os.environ.get("ZTB_AG_2CTA", "1") == "1"
         self._ag_pending = [False] * self.nb
         self.epoch = 0
         self.stream = torch.cuda.Stream(device)
@@ -224,9 +228,9 @@ class FusedComm:
                 self._C.allgather_pull(self.flat_param, self._param.ptrs, segs, n, tiles, 0, 0)
                 self.ready[b].record(self.stream)
 
-    def ag_plan(self, b: int, first_region: str):
+    def ag_plan(self, b: int, first_region: str, tile: int = COPY_TILE):
         """Pull list for bucket ``b`` with ``first_region``'s chunks leading (those gate the GEMM)."""
-        key = (b, first_region)
+        key = (b, first_region, tile)
         if key not in self.ag_lists:
             regs = self.layout.buckets[b].regions
             lead = [r for r in regs if r.name == first_region]
@@ -237,20 +241,21 @@ class FusedComm:
             pl = [(r0.offset + p * r0.chunk, 0, r0.chunk, p) for p in order]
             n_b = len(pl)
             pl += [(r.offset + p * r.chunk, 0, r.chunk, p) for p in order for r in rest]
-            segs, tiles = pack_segments(pl, self.device, COPY_TILE)
+            segs, tiles = pack_segments(pl, self.device, tile)
             k = r0.shape[1]
             ok = r0.padded == r0.numel and (r0.chunk % k == 0)
-            self.ag_lists[key] = dict(segs=segs, nseg=len(pl), n_b=n_b, tiles=tiles, b_tiles=(r0.chunk + COPY_TILE - 1) // COPY_TILE,
+            self.ag_lists[key] = dict(segs=segs, nseg=len(pl), n_b=n_b, tiles=tiles, b_tiles=(r0.chunk + tile - 1) // tile,
                                       rows_per_rank=r0.chunk // k, ok=ok)
         return self.ag_lists[key]
 
     def gemm_ag(self, b: int, first_region: str, x2: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
         """``x2 @ w.T`` where ``w`` is bucket ``b``'s first-consumed weight: the bucket's all-gather
         runs inside the GEMM kernel (compute stream); marks the bucket as gathered."""
-        plan = self.ag_plan(b, first_region)
+        two_cta = self.ag_two_cta and (plan0 := self.ag_plan(b, first_region, AG2_TILE))["rows_per_rank"] % 128 == 0
+        plan = plan0 if two_cta else self.ag_plan(b, first_region)
         out = self._C.gemm_ag(x2, w, self._param.ptrs, self.flat_param, plan["segs"], plan["nseg"], plan["n_b"], plan["tiles"],
                               self._my_row(FLAG_SHARD_READY, b), self.epoch, self.ag_done, plan["b_tiles"], plan["rows_per_rank"],
-                              self.world, self.rank)
+                              self.world, self.rank, two_cta)
         self._ag_pending[b] = False
         self._pending[b] = False
         return out

@@ -141,6 +141,11 @@ class Zero1Engine:
                 p.data = L.view(self.flat_param, n)
                 p.grad = L.view(self.flat_grad, n)
         self._named = named
+        # Lazy zero_grad (first micro-batch overwrites instead of accumulating) is only sound when every parameter's
+        # gradient is produced by a fused writer that honours the overwrite mode.  The op layer falls back to plain
+        # autograd accumulation for shapes its kernels do not take (last dim or vocabulary not a multiple of 8); with such
+        # a parameter the engine keeps the memset.
+        self._lazy_ok = all(p.shape[-1] % 8 == 0 and (p.ndim < 2 or p.shape[0] % 8 == 0) for _, p in named)
         self._grad_shard = torch.zeros(L.shard_total, dtype=self.grad_dtype, device=dev) if backend != "fused" else None
         # fused backend: overlap machinery (see parallel/fused.py)
         self._overwrite_next = False   # first micro-batch of the step overwrites the gradient buffers
@@ -231,7 +236,7 @@ class Zero1Engine:
     def zero_grad(self, lazy: bool = False) -> None:
         """``lazy=True`` (fused backend, gradients produced through ``engine.backward``): skip the
         memset, the next backward overwrites instead of accumulating."""
-        if lazy and self._fused is not None:
+        if lazy and self._fused is not None and self._lazy_ok:
             self._overwrite_next = True
             return
         self.flat_grad.zero_()

@@ -22,7 +22,7 @@ import torch
 
 from .config import DEFAULT_CFG, DEFAULT_MODEL_CFG, Config, flatten_dict, load_config
 from .data.pipeline import (DevicePrefetcher, StreamingTokenDataset, SyntheticTokenDataset, batch_iterator, rechunk,
-                            to_micro_batches)
+                            skip_batches, to_micro_batches)
 from .models.gpt import model_getter
 from .optim.schedule import schedule_from_config
 from .parallel import dist as pdist
@@ -92,6 +92,10 @@ class Trainer:
         if resume:
             self.resume_step = ckpt.resume(self.engine, self.workdir)
             self.log.debug("resuming from step %d", self.resume_step)
+        elif on_gpu:
+            from .ops import cuda as K
+
+            K.manual_seed(int(t.get("seed", 0)) * 1000003 + 0x5EED5EED, env.device)  # dropout streams follow training.seed
         elif cfg.model.get("warm_init", False):
             ckpt.warm_start(self.engine, os.path.join(root, cfg.model.warm_init_dir), bool(cfg.model.get("extend_depth", False)))
             self.log.debug("warm-started from %s", cfg.model.warm_init_dir)
@@ -102,7 +106,8 @@ class Trainer:
             run_cfg.update({"training.local_batch_size": self.rows_per_rank, "runtime": f"b200x{env.world}",
                             "Total Training Tokens": int(t.total_steps) * self.global_tokens_per_step,
                             "Total Devices": env.world})
-            self.sink = MetricsSink(self.workdir, run_cfg, project=str(d.get("wandb_project", "") or ""), enabled=env.is_main)
+            self.sink = MetricsSink(self.workdir, run_cfg, project=str(d.get("wandb_project", "") or ""), enabled=env.is_main,
+                                    run_id=ckpt.stable_run_id(self.workdir) if env.is_main else None)
         self._timer = StepTimer(env.device)
         self._nvtx = on_gpu and os.environ.get("ZTB_NVTX", "0") == "1"   # NVTX ranges for nsys/ncu timelines
         self._graph = None
@@ -110,18 +115,37 @@ class Trainer:
     # ------------------------------------------------------------------ data
     def _samples(self, split: str) -> Iterable[np.ndarray]:
         d, env = self.cfg.data, self.env
+        shuffle = int(d.get("shuffle_buffer", 100000))
+        if split != "train":
+            # validation is re-opened at every evaluation: keep its shuffle buffer (and the refill from disk) small
+            shuffle = min(shuffle, int(d.get("validation_shuffle_buffer", 2048)))
         if self.synthetic:
             return SyntheticTokenDataset(self.model.cfg.vocab_size, self.max_context, rank=env.rank,
                                          seed=int(self.cfg.training.get("seed", 0)) + (0 if split == "train" else 7919))
         idx = d.index_path_train if split == "train" else d.index_path_validation
         return StreamingTokenDataset(idx, max_context=self.max_context, rank=env.rank, world=env.world,
-                                     shuffle_buffer=int(d.get("shuffle_buffer", 100000)),
+                                     shuffle_buffer=shuffle,
                                      seed=23 + self.resume_step,  # reference: Random(23 + resume_step)
                                      epochs=int(self.cfg.training.max_epochs) if split == "train" else 1)
 
-    def train_batches(self) -> Iterator[torch.Tensor]:
+    def train_batches(self) -> DevicePrefetcher:
         it = batch_iterator(self._samples("train"), self.rows_per_rank)
+        if self.resume_step > 0:
+            # fast-forward the stream to where the interrupted run stopped (reference main_zero.py:437,470-471:
+            # resume_step % steps_per_epoch batches are skipped); the synthetic source has no epochs
+            spe = int(self.cfg.data.get("steps_per_epoch", 0) or 0)
+            n = self.resume_step if (self.synthetic or spe <= 0) else self.resume_step % spe
+            it = skip_batches(it, n)
         return DevicePrefetcher(it, self.env.device)
+
+    def _agree_more(self, have: bool) -> bool:
+        """True while EVERY rank still has a batch.  Real shards give ranks different batch counts (striding +
+        drop_last); the first rank to run dry must stop all of them, or the others spin on its GRAD_READY flags."""
+        if self.env.world == 1 or self.synthetic:
+            return have
+        flag = torch.tensor([1 if have else 0], dtype=torch.int32, device=self.env.device)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        return bool(flag.item())
 
     def val_batches(self) -> Iterator[torch.Tensor]:
         rows = max(self.rows_per_rank // 4, 1)  # reference: validation batch = batch_size // 4
@@ -160,10 +184,15 @@ class Trainer:
     def evaluate(self) -> Dict[str, float]:
         t = self.cfg.training
         losses = []
-        for i, b in enumerate(self.val_batches()):
-            if i >= int(t.maximum_evaluation_steps):
-                break
-            losses.append(self.eval_step(b).float())
+        batches = self.val_batches()
+        try:
+            for _ in range(int(t.maximum_evaluation_steps)):
+                b = next(batches, None)
+                if not self._agree_more(b is not None):
+                    break
+                losses.append(self.eval_step(b).float())
+        finally:
+            batches.close()   # stops the producer thread and releases the dataset generator + its shuffle buffer
         if not losses:
             return {}
         loss = pdist.all_reduce_mean(torch.stack(losses).mean().reshape(1).to(self.env.device)).item()
@@ -179,8 +208,12 @@ class Trainer:
         step = self.resume_step
         new_steps = 0
         flops_tok = self.model.cfg.flops_per_token(self.train_context)
-        for batch in self.train_batches():
+        batches = self.train_batches()
+        while True:
             if step >= total_steps or (max_steps is not None and new_steps >= max_steps):
+                break
+            batch = next(batches, None)
+            if not self._agree_more(batch is not None):
                 break
             self._timer.start()
             out = self.train_step(batch)
@@ -205,6 +238,7 @@ class Trainer:
             if env.is_main and (step % 10 == 0 or new_steps <= 3 or do_eval):
                 self.log.debug("step %d loss %.4f lr %.3e %.1f ms %.0f tok/s%s", step, loss, out["lr"], ms, tok_s,
                                f" val {last['validation/loss']:.4f}" if "validation/loss" in last else "")
+        batches.close()
         self.final_step = step
         return last
 

@@ -61,10 +61,50 @@ def wipe_checkpoints(workdir: str) -> None:
             shutil.rmtree(d)
 
 
+def _rng_snapshot(engine):
+    """(seed, offset) of the device-resident Philox state that keys every dropout mask: restored on resume so the
+    continued run draws the masks the uninterrupted run would have drawn (the reference folds resume_step into its
+    key instead, ``main_zero.py:432``)."""
+    if engine.device.type != "cuda":
+        return None
+    from ..ops import cuda as K
+
+    return [int(v) for v in K.rng_state(engine.device).tolist()]
+
+
+def _rng_restore(engine, snap) -> None:
+    if snap is None or engine.device.type != "cuda":
+        return
+    from ..ops import cuda as K
+
+    K.rng_state(engine.device).copy_(torch.tensor([int(snap[0]), int(snap[1])], dtype=torch.int64))
+
+
+def stable_run_id(workdir: str) -> str:
+    """One metrics-run id per checkpoint directory, created on first use and re-read on resume, so a resumed job
+    continues the same W&B run (the reference generates a fresh id on every start, ``main_zero.py:355-356``)."""
+    path = os.path.join(workdir, "run_id.txt")
+    try:
+        with open(path) as f:
+            rid = f.read().strip()
+        if rid:
+            return rid
+    except OSError:
+        pass
+    import uuid
+
+    rid = uuid.uuid4().hex[:8]
+    os.makedirs(workdir, exist_ok=True)
+    with open(path, "w") as f:
+        f.write(rid)
+    return rid
+
+
 def save_checkpoint(engine, workdir: str, step: int, keep: int = 5, sharded: bool = False) -> None:
     """Collective: every rank must call.  Rank 0 writes the consolidated files."""
     pdir, odir = _dirs(workdir)
     rank = engine.rank
+    rng = _rng_snapshot(engine)
     if rank == 0:
         os.makedirs(pdir, exist_ok=True)
         os.makedirs(odir, exist_ok=True)
@@ -74,12 +114,12 @@ def save_checkpoint(engine, workdir: str, step: int, keep: int = 5, sharded: boo
         _atomic_save(engine.shard_state(), os.path.join(odir, f"optimizer_{step}.rank{rank}.pt"))
         params = engine.full_params_fp32(0)
         if rank == 0:
-            _atomic_save({"step": step, "params": params}, os.path.join(pdir, f"params_{step}.pt"))
+            _atomic_save({"step": step, "params": params, "rng": rng, "opt_step": engine.step_count}, os.path.join(pdir, f"params_{step}.pt"))
     else:
         st = engine.consolidated_state(0)
         if rank == 0:
-            _atomic_save({"step": step, "params": st["params"]}, os.path.join(pdir, f"params_{step}.pt"))
-            _atomic_save({"step": step, "exp_avg": st["exp_avg"], "exp_avg_sq": st["exp_avg_sq"]},
+            _atomic_save({"step": step, "params": st["params"], "rng": rng, "opt_step": engine.step_count}, os.path.join(pdir, f"params_{step}.pt"))
+            _atomic_save({"step": step, "opt_step": engine.step_count, "exp_avg": st["exp_avg"], "exp_avg_sq": st["exp_avg_sq"]},
                          os.path.join(odir, f"optimizer_{step}.pt"))
     if rank == 0:
         _prune(pdir, "params_", keep)
@@ -142,20 +182,33 @@ def restore_opt_checkpoint(workdir: str, step: Optional[int] = None, rank: int =
 
 
 def resume(engine, workdir: str, step: Optional[int] = None) -> int:
-    """Load params + optimizer state into the engine and adopt the step."""
-    params, pstep = restore_param_checkpoint(workdir, step)
+    """Load params + optimizer state (+ the dropout RNG position) into the engine and adopt the step.
+    Returns the training step to continue from; the optimizer's own counter (Adam bias correction and LR schedule)
+    is restored separately -- after a warm start the two differ."""
+    pdir = _dirs(workdir)[0]
+    pstep = latest_step(workdir) if step is None else step
+    if pstep is None:
+        raise FileNotFoundError(f"no params_<step>.pt under {pdir}")
+    pst = torch.load(os.path.join(pdir, f"params_{pstep}.pt"), map_location="cpu", weights_only=False)
+    params = pst["params"]
     ost, ostep = restore_opt_checkpoint(workdir, pstep, engine.rank)
     if "master" in ost:  # per-rank shard format
         engine.load_shard_state(ost)
     else:
-        engine.load_consolidated_state({"step": ostep, "params": params, "exp_avg": ost["exp_avg"], "exp_avg_sq": ost["exp_avg_sq"]})
-    return pstep
+        engine.load_consolidated_state({"step": int(ost.get("opt_step", ostep)), "params": params, "exp_avg": ost["exp_avg"], "exp_avg_sq": ost["exp_avg_sq"]})
+    _rng_restore(engine, pst.get("rng"))
+    return int(pstep)
 
 
 def warm_start(engine, warm_dir: str, extend_depth: bool = False) -> None:
-    """Initialise weights (and moments when shapes match) from another run's
-    checkpoint without adopting its step (reference ``cfg.model.warm_init``,
-    ``main_zero.py:268-289``); optional Gopher-style depth extension."""
+    """Initialise weights -- and, when the other run's optimizer checkpoint is there, the Adam moments together with
+    the optimizer's update counter -- from another run's checkpoint (reference ``cfg.model.warm_init``,
+    ``main_zero.py:268-289``); optional Gopher-style depth extension.
+
+    The *training* step stays 0 (data position, logging, total_steps), exactly as in the reference, but the optimizer
+    counter is adopted with the moments: the reference restores ``ScaleByAdamState.count`` and the schedule count next to
+    ``mu`` / ``nu`` (``main_zero.py:105-139``).  Loading warm moments under a count of 0 would divide them by
+    ``1 - beta^t`` with t = 1, 2, ... and inflate the first updates ~2x."""
     from .extend_params import extend_params
 
     params, _ = restore_param_checkpoint(warm_dir)
@@ -163,9 +216,10 @@ def warm_start(engine, warm_dir: str, extend_depth: bool = False) -> None:
     st = {"step": 0, "params": params}
     load_moments = False
     try:
-        ost, _ = restore_opt_checkpoint(warm_dir)
+        ost, ostep = restore_opt_checkpoint(warm_dir)
         if "exp_avg" in ost:
             st["exp_avg"], st["exp_avg_sq"] = ost["exp_avg"], ost["exp_avg_sq"]
+            st["step"] = int(ost.get("opt_step", ostep))
             load_moments = True
     except FileNotFoundError:
         pass
@@ -174,4 +228,4 @@ def warm_start(engine, warm_dir: str, extend_depth: bool = False) -> None:
         if load_moments:
             st["exp_avg"] = extend_params(st["exp_avg"], n_target)
             st["exp_avg_sq"] = extend_params(st["exp_avg_sq"], n_target)
-    engine.load_consolidated_state(st, load_moments=load_moments, adopt_step=False)
+    engine.load_consolidated_state(st, load_moments=load_moments, adopt_step=load_moments)
