@@ -15,8 +15,10 @@ timed with CUDA events (max over ranks):
 
 ``--impl reference`` must run the unmodified reference: it is JAX/TPU-only, has no
 setup.py/pyproject (pip: "not installable") and jax/flax/optax are absent offline, so it
-reports ``unavailable``.  ``--impl baseline`` runs the reference-equivalent stock-PyTorch build
-(cuBLAS + SDPA + NCCL all-reduce/all-gather) for an on-box comparison.
+reports ``unavailable``.  ``--impl baseline`` runs the reference-equivalent stock-library build
+(``baseline/strong.py``: cuBLAS + flash_attn + fused AdamW + one NCCL reduce-scatter / all-gather) for an
+on-box comparison; its committed same-box results (``profiles/baseline_arm.json``) are the denominator
+of ``vs_baseline`` (BASELINE.md publishes no throughput for this config, see its section 2).
 """
 from __future__ import annotations
 
@@ -35,6 +37,7 @@ MODEL = os.environ.get("ZTB_BENCH_MODEL", "1_3b")
 SEQ = int(os.environ.get("ZTB_BENCH_SEQ", "1024"))
 ROWS_PER_GPU = int(os.environ.get("ZTB_BENCH_ROWS", "32"))     # sequences of SEQ tokens per GPU per step
 ACCUM = int(os.environ.get("ZTB_BENCH_ACCUM", "2"))            # micro-batches per step
+MODEL_LABEL = {"1_3b": "1.3B", "760m": "760M", "417m": "417M", "125m": "125M"}
 
 
 def parse():
@@ -85,6 +88,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
+def _baseline_number(world: int):
+    """Same-box result of the stock-library arm for this (model, shape, GPU count), committed under profiles/."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "baseline_arm.json")))
+    except (OSError, ValueError):
+        return None
+    key = f"{MODEL}/seq{SEQ}/rows{ROWS_PER_GPU}/accum{ACCUM}/n{world}"
+    rec = table.get(key)
+    if not rec:
+        return None
+    return {"value": float(rec["value"]), "source": f"profiles/baseline_arm.json[{key}] ({rec.get('note', 'bench.py --impl baseline, same pod')})"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -93,16 +109,11 @@ def main():
         print(json.dumps({"impl": "reference", "unavailable": "reference is JAX/Flax on TPU only (main_zero.py:200-201 raises on GPU); "
                           "no setup.py/pyproject (pip: not installable) and jax/flax/optax/omegaconf are absent offline"}))
         return 0
-    if args.impl == "baseline":
-        os.environ["ZTB_FORCE_REFERENCE"] = "1"
-
     import torch
     import torch.distributed as dist
 
-    from zero_transformer_b200 import ops
     from zero_transformer_b200.config import DEFAULT_MODEL_CFG, load_config
     from zero_transformer_b200.parallel import dist as pdist
-    from zero_transformer_b200.train import Trainer
 
     env = pdist.setup_dp()
     if env.device.type != "cuda":
@@ -110,16 +121,32 @@ def main():
         return 1
     world = env.world
     assert world == args.gpus or world == 1 and args.gpus == 1, f"launched {world} ranks for --gpus {args.gpus}"
-    over = [
-        f"model.size={MODEL}", f"training.batch_size={ROWS_PER_GPU * world}", f"training.train_context={SEQ}",
-        f"data.max_context={SEQ}", f"training.gradient_accumulation_steps={ACCUM}", "training.evaluation_frequency=0",
-        "data.corpus=synthetic", "data.checkpoint_directory=gpurun_out/bench_ckpt",
-        "training.comm_backend=" + ("allreduce" if args.impl == "baseline" else "auto"),
-        "training.grad_dtype=bfloat16",
-    ]
-    cfg = load_config(None, over)
-    tr = Trainer(cfg, DEFAULT_MODEL_CFG, env, log_metrics=False)
-    vocab = tr.model.cfg.vocab_size
+    if args.impl == "baseline":
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        from strong import BaselineTrainer   # stock libraries only: none of this repo's kernels / ops / engine
+
+        tr = BaselineTrainer(MODEL, DEFAULT_MODEL_CFG, env.device, env.rank, world, ACCUM, SEQ)
+        ops = None
+        model_cfg = None
+    else:
+        from zero_transformer_b200 import ops
+        from zero_transformer_b200.train import Trainer
+
+        over = [
+            f"model.size={MODEL}", f"training.batch_size={ROWS_PER_GPU * world}", f"training.train_context={SEQ}",
+            f"data.max_context={SEQ}", f"training.gradient_accumulation_steps={ACCUM}", "training.evaluation_frequency=0",
+            "data.corpus=synthetic", "data.checkpoint_directory=gpurun_out/bench_ckpt",
+            "training.comm_backend=auto", "training.grad_dtype=bfloat16",
+        ]
+        cfg = load_config(None, over)
+        tr = Trainer(cfg, DEFAULT_MODEL_CFG, env, log_metrics=False)
+        model_cfg = tr.model.cfg
+    if model_cfg is None:   # baseline arm: shape and FLOP count from the same YAML table (no model of ours is built)
+        from zero_transformer_b200.config import load_yaml
+        from zero_transformer_b200.models.gpt import _cfg_from_entry
+
+        model_cfg = _cfg_from_entry(load_yaml(DEFAULT_MODEL_CFG)[MODEL], None)
+    vocab = model_cfg.vocab_size
     tokens_per_step = ROWS_PER_GPU * world * SEQ
 
     # ---------------- data: pinned host batches (e2e arm) and resident device batches (device arm)
@@ -171,16 +198,21 @@ def main():
     if env.is_main:
         tok_s = tokens_per_step * args.steps / (ms_dev * 1e-3)
         tok_s_e2e = tokens_per_step * args.steps / (ms_e2e * 1e-3)
-        flops_tok = tr.model.cfg.flops_per_token(SEQ)
+        flops_tok = model_cfg.flops_per_token(SEQ)            # causal attention counted once (lower triangle)
+        flops_tok_dense = model_cfg.flops_per_token(SEQ, causal=False)
+        base = _baseline_number(world)
         from zero_transformer_b200.utils.metrics import measured_peaks
 
         pk = measured_peaks()
         rec = {
-            "metric": "tokens/sec (whole box, max over ranks) GPT-2 1.3B ZeRO-1", "value": round(tok_s, 1), "unit": "tokens/s",
+            "metric": f"tokens/sec (whole box, max over ranks) GPT-2 {MODEL_LABEL.get(MODEL, MODEL)} ZeRO-1", "value": round(tok_s, 1), "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev / args.steps, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": (round(tok_s / base["value"], 3) if base and args.impl == "ours" else None),
+            "vs_baseline_source": (base["source"] if base and args.impl == "ours" else None),
+            "dtype": "bf16", "data": "synthetic",
             "impl": args.impl,
-            "config": {"model": f"gpt2-{MODEL} ALiBi (D=2048,H=16,N=24,V=50304)" if MODEL == "1_3b" else MODEL,
+            "config": {"model": f"gpt2-{MODEL} ALiBi (D={model_cfg.embedding_dim},H={model_cfg.num_head},N={model_cfg.N},V={model_cfg.vocab_size})",
                        "global_batch": ROWS_PER_GPU * world, "seq_len": SEQ, "grad_accum": ACCUM, "dropout": 0.1,
                        "parallelism": f"dp{world}+zero1", "optimizer": "AdamW fp32 master, elementwise clip 1.0",
                        "l2": "working set per step (weights+activations, >30 GB) far exceeds the 126 MB L2; no explicit flush"},
@@ -189,10 +221,12 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "mfu_vs_measured_sustained": round(tok_s / world * flops_tok / (pk.get("bf16_tflops_sustained", 1400.0) * 1e12), 4),
+            "mfu_dense_attention_flops": round(tok_s / world * flops_tok_dense / (pk.get("bf16_tflops_sustained", 1400.0) * 1e12), 4),
             "peaks_source": pk.get("source"),
         }
         print(json.dumps(rec))
-    tr.close()
+    if hasattr(tr, "close"):
+        tr.close()
     pdist.shutdown()
     return 0
 

@@ -8,9 +8,20 @@ Measures, on the GPT-2 1.3B parameter layout (2.62 GB of bf16 gradients / parame
   * the fused reduce-scatter + AdamW kernel (per-step total over all buckets),
   * the all-gather-fused QKV GEMM vs. the plain QKV GEMM (one block bucket).
 All times are CUDA-event times, max over ranks.  "busbw" follows the NCCL convention
-bytes * (n-1)/n / time.  Roofline for a fused kernel = max(HBM time, NVLink time, math time) with the
-measured denominators (HBM copy bandwidth from MEASURED_PEAKS.json, 770 GB/s per direction NVLink,
-cuBLAS bf16 peak).
+bytes * (n-1)/n / time.
+
+ONE roofline per fused kernel (round-1 reported two inconsistent ones): the slower of
+  link   bytes that must cross this GPU's NVLink port in the busier direction / link bandwidth
+  hbm    bytes this GPU's HBM must move / measured copy bandwidth (MEASURED_PEAKS.json)
+  math   FLOPs / measured cuBLAS bf16 burst rate (GEMM-fused kernels only)
+with P = parameter count, n = ranks, bf16 gradients and parameters, fp32 master + 2 moments:
+  fused RS+AdamW+AG, NVLS plane   link: 2P out (the switch pulls every rank's copy of every shard) + 2P/n out (push of
+                                  the new shard); 2P/n + 2P in  ->  2P (1 + 1/n) each way
+                                  hbm : 2P (gradient reads) + 24 P/n (master, m, v read + write) + 2P (gathered params written)
+  fused RS+AdamW, P2P plane       link: 2P (n-1)/n in (peer gradient chunks); hbm: 2P + 24 P/n + 2P/n
+  all-gather pull / AG in GEMM    link: 2 B (n-1)/n in for a bucket of B parameters
+The fraction is reported against the MEASURED link bandwidth (770 GB/s per direction, profiling guide) and, for
+context, against the nominal 900 GB/s.
 """
 import json
 import os
@@ -78,13 +89,33 @@ def main():
             fc.bucket_update(b, **kw)
         torch.cuda.current_stream().wait_stream(fc.stream)
 
-    t = timed(fused_rs_adam)
-    hbm = (2 * L.shard_total * n + 12 * L.shard_total + 14 * L.shard_total) / (pk["hbm_gbs"] * 1e9) * 1e3  # local part of the reads + state
-    nv = wire / (NVLINK_GBS * 1e9) * 1e3
-    if fc.nvls:   # switch-side reduction: the shard comes in once; the push sends the shard out once, (n-1)/n of the model comes in
-        nv = max(2 * L.shard_total, wire) / (NVLINK_GBS * 1e9) * 1e3
-    out["rs_adam_fused"] = {"ms": round(t, 3), "busbw_gbs": round(wire / t / 1e6, 1), "roofline_ms": round(max(hbm, nv), 3),
-                            "roofline_frac": round(max(hbm, nv) / t, 3), "bound": "nvlink" if nv > hbm else "hbm"}
+    P = L.total
+    have_mc = bool(fc.nvls)
+
+    def rs_adam_record(nvls_plane):
+        fc.nvls = nvls_plane
+        t = timed(fused_rs_adam)
+        if nvls_plane:
+            link_bytes = 2 * P * (1 + 1 / n)
+            hbm_bytes = 2 * P + 24 * P / n + 2 * P
+        else:
+            link_bytes = 2 * P * (n - 1) / n
+            hbm_bytes = 2 * P + 24 * P / n + 2 * P / n
+        hbm = hbm_bytes / (pk["hbm_gbs"] * 1e9) * 1e3
+        nv = link_bytes / (NVLINK_GBS * 1e9) * 1e3
+        nv900 = link_bytes / 900e9 * 1e3
+        return {"ms": round(t, 3), "plane": "nvls" if nvls_plane else "p2p", "includes_allgather": bool(nvls_plane),
+                "link_bytes_per_rank_per_direction": int(link_bytes), "hbm_bytes_per_rank": int(hbm_bytes),
+                "link_ms_at_770": round(nv, 3), "link_ms_at_900": round(nv900, 3), "hbm_ms": round(hbm, 3),
+                "roofline_ms": round(max(hbm, nv), 3), "roofline_frac": round(max(hbm, nv) / t, 3),
+                "roofline_frac_vs_900": round(max(hbm, nv900) / t, 3), "bound": "nvlink" if nv > hbm else "hbm",
+                "busbw_gbs": round(wire / t / 1e6, 1)}
+
+    out["rs_adam_fused"] = rs_adam_record(have_mc)            # the default data plane
+    if have_mc:
+        out["rs_adam_fused_p2p"] = rs_adam_record(False)       # same kernel, peer loads instead of the switch reduction
+        fc.nvls = True
+    nv = wire / (NVLINK_GBS * 1e9) * 1e3   # plain reduce-scatter / all-gather rows below: 2P (n-1)/n over the link
 
     if n > 1:
         def ag_pull():
@@ -136,6 +167,9 @@ def main():
             torch.cuda.current_stream().wait_stream(fc.stream)
             fc.gemm_ag(b, name, x, w)
 
+        fc.ag_two_cta = False
+        t_ag1 = timed(ag_gemm)
+        fc.ag_two_cta = True
         t_ag = timed(ag_gemm)
         t_plain = timed(lambda: K._C.gemm(x, w, two_cta=False))
         t_plain2 = timed(lambda: K._C.gemm(x, w, two_cta=True))
@@ -144,7 +178,8 @@ def main():
         fl = 2.0 * Mtok * 3 * D * D
         math_ms = fl / (pk["bf16_tflops"] * 1e12) * 1e3
         nv_ms = bwire / (NVLINK_GBS * 1e9) * 1e3
-        out["ag_gemm_fused"] = {"ms": round(t_ag, 3), "plain_gemm_1cta_ms": round(t_plain, 3), "plain_gemm_2cta_ms": round(t_plain2, 3),
+        out["ag_gemm_fused"] = {"ms": round(t_ag, 3), "kernel": "cta-pair + bulk-copy gather ring", "ms_1cta_register_gather": round(t_ag1, 3),
+                                "vs_plain_2cta": round(t_ag / t_plain2, 3), "plain_gemm_1cta_ms": round(t_plain, 3), "plain_gemm_2cta_ms": round(t_plain2, 3),
                                 "separate_pull_ms": round(t_pull, 3), "bucket_mb": round(bucket_bytes / 1e6, 1),
                                 "roofline_ms": round(max(math_ms, nv_ms), 3), "roofline_frac": round(max(math_ms, nv_ms) / t_ag, 3),
                                 "bound": "nvlink" if nv_ms > math_ms else "math"}

@@ -4,8 +4,8 @@ Capabilities of the reference app (``app.py:30-189``): load a model by size +
 checkpoint path, move to GPU in half precision, stream tokens with a KV cache,
 temperature, repetition penalty, top-k, nucleus (top-p), greedy, EOS stop,
 context cropping to the model's window.  The reference serves this through
-Gradio (not installed here); this module is a CLI and a generator API, and
-``launch_gradio`` wraps the same generator when gradio is importable.
+Gradio; this module is the CLI and the generator API, ``serve.py`` is the browser UI (FastAPI + uvicorn, same controls)
+and ``utils/tokenizer.py`` the GPT-NeoX-compatible byte-level BPE tokenizer.
 """
 from __future__ import annotations
 
@@ -22,26 +22,7 @@ from .utils import checkpoint as ckpt
 from .utils.export import load_reference_pth
 
 
-class ByteTokenizer:
-    """Fallback tokenizer (UTF-8 bytes) for models with a >=256 vocabulary when no
-    HF tokenizer directory is available offline (the reference downloads
-    ``EleutherAI/gpt-neox-20b``, ``app.py:27``)."""
-
-    eos_token_id = 0
-
-    def encode(self, s: str) -> List[int]:
-        return list(s.encode("utf-8"))
-
-    def decode(self, ids) -> str:
-        return bytes(int(i) % 256 for i in ids).decode("utf-8", errors="replace")
-
-
-def load_tokenizer(path: Optional[str]):
-    if path:
-        from transformers import AutoTokenizer
-
-        return AutoTokenizer.from_pretrained(path, local_files_only=True)
-    return ByteTokenizer()
+from .utils.tokenizer import BPETokenizer, ByteTokenizer, load_tokenizer  # noqa: E402,F401  (re-exported: public API of this module)
 
 
 def model_creator(size: str, path: Optional[str], model_cfg: str = DEFAULT_MODEL_CFG, device: Optional[str] = None):
@@ -132,22 +113,11 @@ def generate_text(model, tokenizer, prompt: str, steps: int = 64, **kw) -> str:
     return tokenizer.decode(out)
 
 
-def launch_gradio(model, tokenizer, share: bool = False):  # pragma: no cover - gradio not installed in this image
-    import gradio as gr
+def launch_ui(model, tokenizer, model_name: str = "model", share: bool = False, port: int = 7860):
+    """Serve the browser UI (the reference's Gradio Blocks page, ``app.py:199-261``) with FastAPI + uvicorn."""
+    from .serve import launch
 
-    def fn(prompt, steps, temperature, top_k, top_p, rep, sampling):
-        text = ""
-        for tok in generate_from_prompt(model, tokenizer.encode(prompt), int(steps), temperature=temperature, top_k=int(top_k),
-                                        top_p=top_p, repetition_penalty=rep, sample=(sampling == "sample"),
-                                        eos_token_id=getattr(tokenizer, "eos_token_id", None)):
-            text += tokenizer.decode([tok])
-            yield text
-
-    ui = gr.Interface(fn, [gr.Textbox(lines=4, label="prompt"), gr.Slider(1, 512, 64, step=1, label="steps"),
-                           gr.Slider(0.1, 2.0, 0.8, label="temperature"), gr.Slider(0, 200, 40, step=1, label="top-k"),
-                           gr.Slider(0.0, 1.0, 0.95, label="top-p"), gr.Slider(1.0, 2.0, 1.2, label="repetition penalty"),
-                           gr.Radio(["sample", "greedy"], value="sample")], gr.Textbox(label="completion"))
-    ui.queue().launch(share=share)
+    launch(model, tokenizer, model_name, share=share, port=port)
 
 
 def parse(argv=None):
@@ -155,7 +125,8 @@ def parse(argv=None):
     p.add_argument("--model-size", default="417m")
     p.add_argument("--model-path", default=None)
     p.add_argument("--model-cfg", default=DEFAULT_MODEL_CFG)
-    p.add_argument("--tokenizer", default=None, help="local HF tokenizer directory (default: byte tokenizer)")
+    p.add_argument("--tokenizer", default=None, help="tokenizer.json / tokenizer directory (default: $ZTB_TOKENIZER, cached gpt-neox-20b, else bytes)")
+    p.add_argument("--port", type=int, default=7860)
     p.add_argument("--prompt", default="Hello")
     p.add_argument("--steps", type=int, default=64)
     p.add_argument("--temperature", type=float, default=0.8)
@@ -164,7 +135,7 @@ def parse(argv=None):
     p.add_argument("--repetition-penalty", type=float, default=1.2)
     p.add_argument("--greedy", action="store_true")
     p.add_argument("--seed", type=int, default=None)
-    p.add_argument("--share", action="store_true", help="serve the Gradio UI (needs gradio)")
+    p.add_argument("--share", action="store_true", help="serve the browser UI on 0.0.0.0 (reference flag name)")
     p.add_argument("--ui", action="store_true")
     return p.parse_args(argv)
 
@@ -174,7 +145,7 @@ def main(argv=None):
     model = model_creator(a.model_size, a.model_path, a.model_cfg)
     tok = load_tokenizer(a.tokenizer)
     if a.ui or a.share:
-        return launch_gradio(model, tok, a.share)
+        return launch_ui(model, tok, a.model_size, a.share, a.port)
     sys.stdout.write(a.prompt)
     for t in generate_from_prompt(model, tok.encode(a.prompt), a.steps, temperature=a.temperature, top_k=a.top_k,
                                   top_p=a.top_p, repetition_penalty=a.repetition_penalty, sample=not a.greedy,
