@@ -44,7 +44,7 @@ std::vector<at::Tensor> layernorm_bwd(const at::Tensor& dy, const at::Tensor& x,
                                       const at::Tensor& rstd, const c10::optional<at::Tensor>& dres,
                                       const c10::optional<at::Tensor>& grad_out, bool accumulate,
                                       const c10::optional<at::Tensor>& scratch, const c10::optional<at::Tensor>& ticket,
-                                      double drop_p, const c10::optional<at::Tensor>& rng, int64_t op_id) {
+                                      double drop_p, const c10::optional<at::Tensor>& rng, int64_t op_id, bool deterministic) {
   need(is_bf16_cuda(dy) && is_bf16_cuda(x) && dy.is_contiguous() && x.is_contiguous(), "layernorm_bwd: bf16 contiguous");
   c10::cuda::CUDAGuard g(x.device());
   int D = x.size(-1);
@@ -53,7 +53,7 @@ std::vector<at::Tensor> layernorm_bwd(const at::Tensor& dy, const at::Tensor& x,
   const void* dr = nullptr;
   if (dres.has_value()) { need(is_bf16_cuda(*dres) && dres->is_contiguous() && dres->numel() == x.numel(), "layernorm_bwd: bad dres"); dr = dres->data_ptr(); }
   ZtbLnBwdExtra ex{};
-  at::Tensor dw, dmask;
+  at::Tensor dw, dmask, partials;
   float* dwp = nullptr;
   if (grad_out.has_value()) {
     need(scratch.has_value() && ticket.has_value(), "layernorm_bwd: grad_out needs scratch + ticket");
@@ -65,6 +65,10 @@ std::vector<at::Tensor> layernorm_bwd(const at::Tensor& dy, const at::Tensor& x,
     ex.ticket = reinterpret_cast<unsigned int*>(ticket->data_ptr());
     dwp = scratch->data_ptr<float>();
     dw = at::empty({0}, x.options().dtype(at::kFloat));
+    if (deterministic) {
+      partials = at::empty({(int64_t)ztb_layernorm_bwd_grid(M, D, num_sms()), (int64_t)D}, x.options().dtype(at::kFloat));
+      ex.partials = partials.data_ptr<float>();
+    }
   } else {
     dw = at::empty({D}, x.options().dtype(at::kFloat));
     dwp = dw.data_ptr<float>();
@@ -332,7 +336,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("layernorm_fwd", &layernorm_fwd);
   m.def("layernorm_bwd", &layernorm_bwd, py::arg("dy"), py::arg("x"), py::arg("w"), py::arg("mean"), py::arg("rstd"), py::arg("dres") = py::none(),
         py::arg("grad_out") = py::none(), py::arg("accumulate") = false, py::arg("scratch") = py::none(), py::arg("ticket") = py::none(),
-        py::arg("drop_p") = 0.0, py::arg("rng") = py::none(), py::arg("op_id") = 0);
+        py::arg("drop_p") = 0.0, py::arg("rng") = py::none(), py::arg("op_id") = 0, py::arg("deterministic") = false);
   m.def("dropout_add", &dropout_add);
   m.def("embedding_fwd", &embedding_fwd);
   m.def("embedding_bwd_", &embedding_bwd_);

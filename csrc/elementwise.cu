@@ -69,6 +69,8 @@ struct LnBwdExtra {
   int grad_fp32;         // dtype of grad_out
   int grad_accumulate;   // += instead of =
   unsigned int* ticket;  // finished-block counter (zero on entry, zero on exit)
+  float* partials;       // optional [gridDim.x, D]: deterministic mode -- per-block partial sums, added up in block order by
+                         // the last block instead of meeting through fp32 atomics (whose order changes run to run)
   bf16* dmask;           // optional [M, D]
   float p, inv_keep;
   const uint64_t* rng;
@@ -84,8 +86,14 @@ ZTB_DEVINL void ln_bwd_finalize(float* dw, int D, const LnBwdExtra& ex, bool* is
   if (!*is_last) return;
   __threadfence();
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float s = __ldcg(dw + c);
-    dw[c] = 0.f;
+    float s;
+    if (ex.partials != nullptr) {
+      s = 0.f;
+      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(ex.partials + (size_t)b * D + c);
+    } else {
+      s = __ldcg(dw + c);
+      dw[c] = 0.f;
+    }
     if (ex.grad_fp32) {
       float* g = reinterpret_cast<float*>(ex.grad_out) + c;
       *g = ex.grad_accumulate ? *g + s : s;
@@ -175,7 +183,11 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
 #pragma unroll
     for (int k = 0; k < 8; ++k) red[warp][(i * 32 + lane) * 8 + k] = acc[i * 8 + k];
   __syncthreads();
-  for (int c = threadIdx.x; c < D; c += 128) atomicAdd(dw + c, red[0][c] + red[1][c] + red[2][c] + red[3][c]);
+  if (ex.partials != nullptr) {
+    for (int c = threadIdx.x; c < D; c += 128) ex.partials[(size_t)blockIdx.x * D + c] = red[0][c] + red[1][c] + red[2][c] + red[3][c];
+  } else {
+    for (int c = threadIdx.x; c < D; c += 128) atomicAdd(dw + c, red[0][c] + red[1][c] + red[2][c] + red[3][c]);
+  }
   ln_bwd_finalize(dw, D, ex, &is_last);
 }
 
@@ -496,6 +508,7 @@ int ztb_layernorm_bwd(const void* dy, const void* x, const void* w, const float*
   if (extra != nullptr) {
     ex.grad_out = extra->grad_out; ex.grad_fp32 = extra->grad_fp32; ex.grad_accumulate = extra->grad_accumulate;
     ex.ticket = extra->ticket; ex.dmask = (bf16*)extra->dmask; ex.p = extra->p;
+    ex.partials = ln_fast(D) ? extra->partials : nullptr;   // the generic (odd-D) kernel keeps its per-element atomics
     ex.inv_keep = extra->p < 1.f ? 1.f / (1.f - extra->p) : 0.f; ex.rng = extra->rng; ex.op_id = extra->op_id;
   }
   if (ex.ticket == nullptr) ZTB_CUDA_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * D, st));   // one-shot scratch: caller owns dw
@@ -508,6 +521,8 @@ int ztb_layernorm_bwd(const void* dy, const void* x, const void* w, const float*
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
+
+int ztb_layernorm_bwd_grid(int M, int D, int sms) { return ln_fast(D) ? grid_for((M + 3) / 4, 1, sms * 4) : M; }
 
 int ztb_dropout_add(const void* y, const void* res, void* out, size_t n, float p, const uint64_t* rng, uint32_t op_id,
                     int sms, cudaStream_t st) {

@@ -15,11 +15,13 @@ int ztb_layernorm_fwd(const void* x, const void* w, void* y, float* mean, float*
 // dropout-masked copy of dx (mask of the dropout+residual op that produced the LayerNorm input).
 struct ZtbLnBwdExtra {
   void* grad_out; int grad_fp32; int grad_accumulate; unsigned int* ticket;
+  float* partials;   // optional [ztb_layernorm_bwd_grid(M, D, sms), D]: order-fixed (bitwise reproducible) weight-gradient reduction
   void* dmask; float p; const uint64_t* rng; uint32_t op_id;
 };
 int ztb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
                       float* dw, int M, int D, int sms, cudaStream_t st, const void* dres = nullptr,
                       const ZtbLnBwdExtra* extra = nullptr);
+int ztb_layernorm_bwd_grid(int M, int D, int sms);
 int ztb_dropout_add(const void* y, const void* res, void* out, size_t n, float p, const uint64_t* rng, uint32_t op_id,
                     int sms, cudaStream_t st);
 int ztb_embedding_fwd(const int* idx, const void* wte, void* out, int M, int D, int V, cudaStream_t st);

@@ -189,3 +189,75 @@ def test_train_cli_on_gpu_with_eval_checkpoint_resume(tmp_path):
     assert train.main(["--resume", *args]) == 0
     recs = [json.loads(l) for l in open(ck / "metrics.jsonl") if '"step"' in l]
     assert [r["step"] for r in recs][-2:] == [3, 4]
+
+
+def test_fp32_main_gradients_match_bf16_gradients():
+    """grad_dtype=float32: the wgrad GEMM epilogues, LayerNorm / embedding backward write into an fp32 flat buffer that
+    is NOT param.grad; the trajectory must track the bf16-gradient engine and the accumulated gradient must be closer to
+    an fp32 accumulation than the bf16 buffer is."""
+    from zero_transformer_b200.optim.schedule import WarmupCosine
+    from zero_transformer_b200.parallel.zero1 import Zero1Engine
+
+    res = {}
+    for gd in (torch.bfloat16, torch.float32):
+        m, _, cfg = _models(dropout=0.0)
+        m = m.float()
+        eng = Zero1Engine(m, lr_fn=WarmupCosine(1e-3, 0, 100, 1e-4), backend="fused", grad_accum_steps=4, grad_dtype=gd)
+        assert eng.flat_grad.dtype == gd
+        g = torch.Generator().manual_seed(3)
+        losses = []
+        for _ in range(3):
+            x = torch.randint(0, cfg.vocab_size, (8, 256), generator=g, dtype=torch.int32).cuda()
+            eng.zero_grad(lazy=True)
+            for k, mb in enumerate(x.chunk(4)):
+                loss = m.loss(mb, train=False)
+                eng.backward(loss, last=(k == 3))
+            losses.append(loss.item())
+            if gd == torch.float32:
+                assert all(p.grad is None for p in m.parameters())
+            eng.step()
+        eng.synchronize()
+        res[gd] = (eng.master.clone(), losses, eng.flat_grad.float().clone())
+    rel = (res[torch.bfloat16][0] - res[torch.float32][0]).norm() / res[torch.float32][0].norm()
+    assert rel < 5e-3, rel.item()
+    assert res[torch.bfloat16][1] == pytest.approx(res[torch.float32][1], rel=2e-2)
+    relg = (res[torch.bfloat16][2] - res[torch.float32][2]).norm() / res[torch.float32][2].norm()
+    assert 0 < relg < 5e-2, relg.item()
+
+
+def test_resume_is_bit_exact_with_dropout(tmp_path):
+    """train 4 steps == train 2 steps + checkpoint + resume 2 steps, dropout ON: needs the data stream fast-forwarded,
+    the Philox (seed, offset) restored and the optimizer counter adopted (reference main_zero.py:432,437,470-471)."""
+    import json
+
+    import zero_transformer_b200.ops.cuda as C
+    from zero_transformer_b200 import train
+
+    C.CONFIG.deterministic = True   # order-fixed LayerNorm weight-gradient reduction; T = 256 keeps attention dQ at <= 2 addends
+    try:
+        _resume_body(tmp_path, train, json)
+    finally:
+        C.CONFIG.deterministic = False
+
+
+def _resume_body(tmp_path, train, json):
+    def run(root, *extra):
+        args = ["--synthetic", "model.size=125m", "training.batch_size=8", "training.train_context=256", "data.max_context=256",
+                "training.gradient_accumulation_steps=2", "training.evaluation_frequency=2", "training.maximum_evaluation_steps=1",
+                "training.warmup_steps=2", "training.total_steps=4", f"data.bucket_path={root}", *extra]
+        assert train.main(args) == 0
+        ck = root / "checkpoints"
+        recs = [json.loads(l) for l in open(ck / "metrics.jsonl") if '"step"' in l]
+        return {r["step"]: r["train/loss"] for r in recs}, torch.load(ck / "params" / "params_4.pt", weights_only=False)
+
+    a_root, b_root = tmp_path / "a", tmp_path / "b"
+    a_root.mkdir(); b_root.mkdir()
+    la, pa = run(a_root)
+    train.main(["--synthetic", "model.size=125m", "training.batch_size=8", "training.train_context=256", "data.max_context=256",
+                "training.gradient_accumulation_steps=2", "training.evaluation_frequency=2", "training.maximum_evaluation_steps=1",
+                "training.warmup_steps=2", "training.total_steps=4", f"data.bucket_path={b_root}", "--max-steps", "2"])
+    lb, pb = run(b_root, "--resume")
+    assert la[3] == lb[3] and la[4] == lb[4], (la, lb)
+    for n in pa["params"]:
+        assert torch.equal(pa["params"][n], pb["params"][n]), n
+    assert pa["rng"] == pb["rng"]

@@ -77,6 +77,9 @@ class _Config:
     fuse_wgrad = os.environ.get("ZTB_FUSE_WGRAD", "1") == "1"    # accumulate dW into param.grad in the epilogue
     gemm_2cta = os.environ.get("ZTB_GEMM_2CTA", "1") == "1"      # cta_group::2 256x256 kernel for the big GEMMs
     attn_impl = os.environ.get("ZTB_ATTN", "auto")                # auto | tc (own kernel) | flash (flash_attn library) | ref
+    # order-fixed reductions where the fast path uses atomics (LayerNorm weight gradient): bitwise run-to-run
+    # reproducibility for T <= 256 (longer sequences: attention dQ has > 2 reduce-add contributions per element)
+    deterministic = os.environ.get("ZTB_DETERMINISTIC", "0") == "1"
     embedding_bwd_sorted = os.environ.get("ZTB_EMB_BWD_SORTED", "1") == "1"  # fp32 per-token sums, one add per gradient row
     fold_dropout_bwd = os.environ.get("ZTB_FOLD_DROPOUT_BWD", "1") == "1"  # LayerNorm-backward emits the masked gradient
 
@@ -243,7 +246,7 @@ def _ln_backward(ctx, dy, dres):
     kw = {}
     if tgt is not None:
         scratch, ticket = _ln_scratch(x.device, x.shape[-1])
-        kw.update(grad_out=tgt, accumulate=GRAD_MODE["accumulate"], scratch=scratch, ticket=ticket)
+        kw.update(grad_out=tgt, accumulate=GRAD_MODE["accumulate"], scratch=scratch, ticket=ticket, deterministic=CONFIG.deterministic)
     if ctx.drop is not None:
         kw.update(drop_p=ctx.drop[0], rng=rng_state(x.device), op_id=ctx.drop[1])
     dx, dw, dmask = _C.layernorm_bwd(dy.contiguous(), x, w.contiguous(), mean, rstd, dr, **kw)

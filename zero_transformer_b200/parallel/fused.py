@@ -197,7 +197,7 @@ class FusedComm:
         """Phase 1 of a two-phase update (global-norm clipping): reduce-scatter bucket ``b`` over peer memory,
         leaving the sum in this rank's own chunk of the local gradient buffer."""
         if self.grad_fp32:
-            raise NotImplementedError("two-phase update needs bf16 gradient buffers")
+            raise NotImplementedError("two-phase update (global-norm clipping) needs bf16 gradient buffers")
         e = self.epoch
         self._ev.record(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):

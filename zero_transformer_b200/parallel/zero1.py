@@ -99,10 +99,14 @@ class Zero1Engine:
         src_dtype = named[0][1].dtype
         self.compute_dtype = compute_dtype or (torch.bfloat16 if dev.type == "cuda" else src_dtype)
         self.grad_dtype = grad_dtype or self.compute_dtype
-        if self.grad_dtype != self.compute_dtype:
-            # autograd requires param.grad to share the parameter's dtype; the reference accumulates
-            # bf16 gradients as well (xmap_train_functions.py:62)
-            raise ValueError("grad_dtype must equal compute_dtype (fp32 main-grads are not implemented)")
+        # grad_dtype != compute_dtype = fp32 "main gradients" next to bf16 parameters.  autograd insists that
+        # param.grad has the parameter's dtype, so the fp32 flat buffer is NOT exposed as .grad: every parameter gets a
+        # ``_ztb_main_grad`` view instead, which the op layer's fused gradient writers target (wgrad GEMM epilogue with an
+        # fp32 C, LayerNorm / embedding backward).  The reference accumulates in bf16 (xmap_train_functions.py:62-70);
+        # this is the SURVEY 7.1 option for long accumulation chains.
+        self.main_grads = self.grad_dtype != self.compute_dtype
+        if self.main_grads and (self.grad_dtype != torch.float32 or dev.type != "cuda"):
+            raise ValueError("main gradients are fp32 next to bf16 parameters on a CUDA device")
         if decay_mask is None:
             decay_mask = model.decay_mask() if hasattr(model, "decay_mask") else {n: p.ndim >= 2 for n, p in named}
         self.layout = FlatLayout([(n, tuple(p.shape)) for n, p in named], decay_mask, self.world, bucket_of)
@@ -139,13 +143,19 @@ class Zero1Engine:
                 self.master[r.shard_offset: r.shard_offset + r.chunk].copy_(full[s: s + r.chunk])
                 self.flat_param[r.offset: r.offset + r.padded].copy_(full.to(self.compute_dtype))
                 p.data = L.view(self.flat_param, n)
-                p.grad = L.view(self.flat_grad, n)
+                if self.main_grads:
+                    p.grad = None
+                    p._ztb_main_grad = L.view(self.flat_grad, n)
+                else:
+                    p.grad = L.view(self.flat_grad, n)
         self._named = named
         # Lazy zero_grad (first micro-batch overwrites instead of accumulating) is only sound when every parameter's
         # gradient is produced by a fused writer that honours the overwrite mode.  The op layer falls back to plain
         # autograd accumulation for shapes its kernels do not take (last dim or vocabulary not a multiple of 8); with such
         # a parameter the engine keeps the memset.
         self._lazy_ok = all(p.shape[-1] % 8 == 0 and (p.ndim < 2 or p.shape[0] % 8 == 0) for _, p in named)
+        if self.main_grads and not self._lazy_ok:
+            raise ValueError("fp32 main gradients need every parameter to have a fused gradient writer (dims multiple of 8)")
         self._grad_shard = torch.zeros(L.shard_total, dtype=self.grad_dtype, device=dev) if backend != "fused" else None
         # fused backend: overlap machinery (see parallel/fused.py)
         self._overwrite_next = False   # first micro-batch of the step overwrites the gradient buffers
@@ -218,6 +228,7 @@ class Zero1Engine:
         is done.  Plain ``loss.backward()`` + ``step()`` remains valid (no overlap)."""
         if self._fused is None:
             loss.backward()
+            self._fold_stray_grads()
             return
         from ..ops import cuda as K
 
@@ -232,6 +243,17 @@ class Zero1Engine:
             K.GRAD_MODE["accumulate"] = True
             self._in_engine_backward = False
         self._overwrite_next = False
+        self._fold_stray_grads()
+
+    def _fold_stray_grads(self) -> None:
+        """Main-gradient mode: a gradient that reached a parameter through plain autograd (an op without a fused
+        writer) sits in ``.grad`` in the compute dtype -- add it to the fp32 buffer and drop it."""
+        if not self.main_grads:
+            return
+        for _, p in self._named:
+            if p.grad is not None:
+                p._ztb_main_grad.add_(p.grad.to(p._ztb_main_grad.dtype))
+                p.grad = None
 
     def zero_grad(self, lazy: bool = False) -> None:
         """``lazy=True`` (fused backend, gradients produced through ``engine.backward``): skip the
@@ -240,6 +262,8 @@ class Zero1Engine:
             self._overwrite_next = True
             return
         self.flat_grad.zero_()
+        if self.main_grads:
+            return
         # autograd may have replaced .grad if someone set it to None; re-point cheaply
         for n, p in self._named:
             if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + self.layout.by_name[n].offset * self.flat_grad.element_size():
