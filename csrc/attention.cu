@@ -586,254 +586,6 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 // =====================================================================================
-// Forward, ping-pong variant (head_dim 128, T % 256 == 0): one CTA owns TWO adjacent 128-query tiles
-// of a (batch, head).  Both tiles consume the same K_j / V_j (single-buffered, separately released:
-// K after the two S MMAs, V after the two PV MMAs, so the next K/V loads overlap the softmax), and
-// each tile has its own softmax warpgroup (one query row per thread).  While warpgroup A runs the
-// softmax of its tile the tensor core works on tile B and vice versa -- the FA3/FA4 ping-pong --
-// instead of idling through the S -> softmax -> P -> PV dependency chain of a single tile.
-//   warps 0-3  softmax tile A      warps 4-7  softmax tile B      warp 8 TMA      warp 9 MMA
-// TMEM: S_A, S_B (2 x 128 columns) + O_A, O_B (2 x 128 columns) = 512 columns.
-constexpr int ATT2_THREADS = 384;
-
-struct Attn2Smem {
-  static constexpr int TILE = 32768;                 // [128 x 128] bf16
-  static constexpr int Q_OFF = 0;                    // 2 tiles
-  static constexpr int K_OFF = 2 * TILE, V_OFF = 3 * TILE;
-  static constexpr int P_OFF = 4 * TILE;             // 2 tiles (also O staging)
-  static constexpr int BAR_OFF = 6 * TILE;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
-};
-
-__global__ void __launch_bounds__(ATT2_THREADS, 1)
-attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
-  constexpr int HD = 128;
-  using L = Attn2Smem;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smQ = smem + L::Q_OFF;
-  uint8_t* smK = smem + L::K_OFF;
-  uint8_t* smV = smem + L::V_OFF;
-  uint8_t* smP = smem + L::P_OFF;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* q_full = bars;           // 1
-  uint64_t* k_full = bars + 1;       // 1
-  uint64_t* k_empty = bars + 2;      // 1
-  uint64_t* v_full = bars + 3;       // 1
-  uint64_t* v_empty = bars + 4;      // 1
-  uint64_t* s_full = bars + 5;       // 2 (per tile)
-  uint64_t* s_empty = bars + 7;      // 2, count 128
-  uint64_t* p_ready = bars + 9;      // 2, count 128
-  uint64_t* pv_done = bars + 11;     // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pr = gridDim.x - 1 - blockIdx.x;          // pair index, heavy first
-  const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
-  const int D = p.H * HD;
-  const int qb0 = 2 * pr;                              // tile A = q block qb0, tile B = qb0 + 1
-  const int nblk = qb0 + 2;                            // KV blocks 0 .. qb0+1 (tile A stops at qb0)
-  const int row0 = b * p.T + qb0 * ATT_BM;
-  const int colQ = h * HD, colK = D + h * HD, colV = 2 * D + h * HD;
-
-  if (warp == 8 && lane == 0) { prefetch_tmap(&tmQKV); prefetch_tmap(&tmO); }
-  if (warp == 9 && lane == 0) {
-    mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); mbar_init(&p_ready[i], 128); mbar_init(&pv_done[i], 1); }
-    fence_barrier_init();
-  }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 8 && lane == 0) {
-      // ===================================================== TMA producer
-      mbar_expect_tx(q_full, 2 * L::TILE);
-#pragma unroll
-      for (int t = 0; t < 2; ++t)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) tma_load_2d(smQ + t * L::TILE + c * 16384, &tmQKV, q_full, colQ + c * 64, row0 + t * ATT_BM);
-      for (int j = 0; j < nblk; ++j) {
-        const int krow = b * p.T + j * ATT_BN;
-        mbar_wait(k_empty, (j & 1) ^ 1);
-        mbar_expect_tx(k_full, L::TILE);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) tma_load_2d(smK + c * 16384, &tmQKV, k_full, colK + c * 64, krow);
-        mbar_wait(v_empty, (j & 1) ^ 1);
-        mbar_expect_tx(v_full, L::TILE);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) tma_load_2d(smV + c * 16384, &tmQKV, v_full, colV + c * 64, krow);
-      }
-    } else if (warp == 9 && lane == 0) {
-      // ===================================================== MMA issuer
-      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, HD, 0, 1);
-      const uint32_t k_addr = smem_u32(smK), v_addr = smem_u32(smV);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < nblk; ++j) {
-        const int nt = (j <= qb0) ? 2 : 1;             // tile A has no work in the last block
-        const int t0 = (j <= qb0) ? 0 : 1;
-        mbar_wait(k_full, j & 1);
-        for (int t = t0; t < 2; ++t) {
-          const int jt = j;                            // tile-local block counter == j (tiles start at 0)
-          mbar_wait(&s_empty[t], (jt & 1) ^ 1);
-          tc_fence_after_sync();
-          const uint32_t q_addr = smem_u32(smQ + t * L::TILE);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k) {
-            const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-            umma_f16_ss(tmem_base + t * 128, make_smem_desc(q_addr + off, 16, 1024, kSwizzle128B),
-                        make_smem_desc(k_addr + off, 16, 1024, kSwizzle128B), idesc_s, k != 0);
-          }
-          umma_commit(&s_full[t]);
-        }
-        umma_commit(k_empty);
-        mbar_wait(v_full, j & 1);
-        for (int t = t0; t < 2; ++t) {
-          mbar_wait(&p_ready[t], j & 1);
-          tc_fence_after_sync();
-          const uint32_t p_addr = smem_u32(smP + t * L::TILE);
-#pragma unroll
-          for (int k = 0; k < ATT_BN / 16; ++k) {
-            uint64_t da = make_smem_desc(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, kSwizzle128B);
-            uint64_t db = make_smem_desc(v_addr + k * 2048, 16384, 1024, kSwizzle128B);
-            umma_f16_ss(tmem_base + 256 + t * 128, da, db, idesc_o, (j | k) != 0);
-          }
-          umma_commit(&pv_done[t]);
-        }
-        umma_commit(v_empty);
-        (void)nt;
-      }
-    }
-  } else {
-    // ===================================================== softmax warpgroups (tile t = warp / 4)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int t = warp >> 2;
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const int qb = qb0 + t;
-    const int qi = qb * ATT_BM + r;
-    const int myblk = qb + 1;                          // this tile's KV blocks 0..qb
-    const uint32_t tS = tmem_base + t * 128, tO = tmem_base + 256 + t * 128;
-    uint8_t* myP = smP + t * L::TILE;
-    const float slope2 = p.slopes ? p.slopes[h] * 1.4426950408889634f : 0.f;
-    const bool use_drop = p.drop_thr8 != 0;
-    uint64_t seed = 0, stream = 0;
-    if (use_drop) { seed = p.rng[0]; stream = p.rng[1] * 65536ull + p.op_id; }
-    Philox ph(seed);
-    const uint64_t row_id = (uint64_t)bh * p.T + qi;
-    float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < myblk; ++j) {
-      mbar_wait(&s_full[t], j & 1);
-      tc_fence_after_sync();
-      float s[128];
-      {
-        uint32_t* sr = reinterpret_cast<uint32_t*>(s);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tS + lane_addr + c * 32, sr + c * 32);
-        tmem_wait_ld();
-      }
-      tc_fence_before_sync();
-      mbar_arrive(&s_empty[t]);
-      const float base = slope2 * (float)(j * ATT_BN - qi);
-      const bool diag = (j == qb);
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 128; ++c) {
-        float v = fmaf(s[c], p.scale_log2, fmaf(slope2, (float)c, base));
-        if (diag && c > r) v = -INFINITY;
-        s[c] = v;
-        mx = fmaxf(mx, v);
-      }
-      float alpha = 1.f;
-      if (mx > m + 8.f) { alpha = ex2_ftz(m - mx); m = mx; }
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < 128; ++c) { s[c] = ex2_ftz(s[c] - m); sum += s[c]; }
-      l = l * alpha + sum;
-      if (j > 0) {
-        mbar_wait(&pv_done[t], (j - 1) & 1);           // P smem free, O stable
-        tc_fence_after_sync();
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(tO + lane_addr + c * 32, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
-            tmem_st_32x32b_x32(tO + lane_addr + c * 32, o);
-          }
-          tmem_wait_st();
-        }
-      }
-      uint8_t* prow = myP + r * 128;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {                    // 16 keys per group -> two 16-byte stores
-        uint32_t pk[8];
-        if (use_drop) {
-          uint4 rb = attn_dropout_bits(ph, row_id, (uint32_t)(j * 8 + g), stream);
-          uint32_t w[4] = {rb.x, rb.y, rb.z, rb.w};
-#pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            uint32_t b0 = (w[e >> 2] >> ((e & 3) * 8)) & 0xFF, b1 = (w[(e + 1) >> 2] >> (((e + 1) & 3) * 8)) & 0xFF;
-            pk[e >> 1] = pack_bf16(b0 >= p.drop_thr8 ? s[g * 16 + e] : 0.f, b1 >= p.drop_thr8 ? s[g * 16 + e + 1] : 0.f);
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) pk[e] = pack_bf16(s[g * 16 + 2 * e], s[g * 16 + 2 * e + 1]);
-        }
-        const int c16 = g * 2;
-        sts_v4(prow + (c16 >> 3) * 16384 + (((c16 & 7) ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-        sts_v4(prow + ((c16 + 1) >> 3) * 16384 + ((((c16 + 1) & 7) ^ (r & 7)) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
-      }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      mbar_arrive(&p_ready[t]);
-    }
-    // ---- epilogue of this tile
-    mbar_wait(&pv_done[t], (myblk - 1) & 1);
-    tc_fence_after_sync();
-    const float inv = (use_drop ? p.inv_keep : 1.f) / l;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t o[32];
-      tmem_ld_32x32b_x32(tO + lane_addr + c * 32, o);
-      tmem_wait_ld();
-      uint8_t* orow = myP + (c >> 1) * 16384 + r * 128;
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        uint4 o4 = make_uint4(pack_bf16(__uint_as_float(o[q4 * 8 + 0]) * inv, __uint_as_float(o[q4 * 8 + 1]) * inv),
-                              pack_bf16(__uint_as_float(o[q4 * 8 + 2]) * inv, __uint_as_float(o[q4 * 8 + 3]) * inv),
-                              pack_bf16(__uint_as_float(o[q4 * 8 + 4]) * inv, __uint_as_float(o[q4 * 8 + 5]) * inv),
-                              pack_bf16(__uint_as_float(o[q4 * 8 + 6]) * inv, __uint_as_float(o[q4 * 8 + 7]) * inv));
-        sts_v4(orow + ((((c & 1) * 4 + q4) ^ (r & 7)) << 4), o4);
-      }
-    }
-    p.lse[(size_t)bh * p.T + qi] = (m + log2f(l)) * 0.6931471805599453f;
-    fence_proxy_async_smem();
-    named_bar_sync(1 + t, 128);
-    if (quarter == 0 && lane == 0) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c) tma_store_2d(&tmO, myP + c * 16384, colQ + c * 64, row0 + t * ATT_BM);
-      tma_commit_group();
-      tma_wait_group<0>();
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after_sync();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-// =====================================================================================
 // Backward.  One CTA per (batch, head, 128-key block j); K_j and V_j stay resident in smem and the
 // CTA walks the query blocks i >= j.  Per (i, j) pair, five tcgen05 GEMMs:
 //     S  = Q_i K_j^T                    -> TMEM[0:128)         (softmax recomputed from the saved LSE)
@@ -861,6 +613,9 @@ struct AttnBwdParams {
   const float* delta;    // [B,H,T] rowsum(dO o O)
   bf16* dqkv;            // [B*T, 3*H*hd] (direct stores for a partial 64-column chunk)
   unsigned long long* dbg;  // optional: per-phase cycle counters of softmax thread 0 (bench/attn_timing.py)
+  int dq_bf16;           // head_dim 128 only: dQ partial sums meet in the bf16 dqkv buffer (bf16 TMA reduce-add, Q columns zeroed by
+                         // the launcher) instead of an fp32 scratch + convert pass: half the reduce traffic, no zero-fill of 4 B/elt,
+                         // no convert kernel; costs one bf16 rounding per key block (<= T/128) instead of one at the end
   uint32_t drop_thr8;
   float inv_keep;
   const uint64_t* rng;
@@ -1153,29 +908,54 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       long long tk5 = clock64();
       tc_fence_after_sync();
       const int qrow0 = b * p.T + qb * ATT_BM;
+      const bool dq16 = HD == 128 && p.dq_bf16;
+      if (dq16) {
+        // bf16 path: this half's 64 columns become one 128-byte row of its staging buffer (64-column bf16 box)
 #pragma unroll
-      for (int c32 = 0; c32 < 2; ++c32) {
-        if (c32 * 32 >= hcn) break;
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(tDP + lane_addr + hc0 + c32 * 32, o);
-        tmem_wait_ld();
-        if (hf && c32 == 0) mbar_wait(dk_done, phs);   // half 1 stages into the dS buffer, which the dK MMA is still reading
-        uint8_t* orow = stage + c32 * 16384 + r * 128;
+        for (int c32 = 0; c32 < 2; ++c32) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(tDP + lane_addr + hc0 + c32 * 32, o);
+          tmem_wait_ld();
+          if (hf && c32 == 0) mbar_wait(dk_done, phs);   // half 1 stages into the dS buffer, which the dK MMA is still reading
+          uint8_t* orow = stage + r * 128;
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4)
-          sts_v4(orow + ((q4 ^ (r & 7)) << 4), make_uint4(o[q4 * 4], o[q4 * 4 + 1], o[q4 * 4 + 2], o[q4 * 4 + 3]));
+          for (int q4 = 0; q4 < 4; ++q4)
+            sts_v4(orow + (((c32 * 4 + q4) ^ (r & 7)) << 4),
+                   make_uint4(pack_bf16(__uint_as_float(o[q4 * 8 + 0]), __uint_as_float(o[q4 * 8 + 1])),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 2]), __uint_as_float(o[q4 * 8 + 3])),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 4]), __uint_as_float(o[q4 * 8 + 5])),
+                              pack_bf16(__uint_as_float(o[q4 * 8 + 6]), __uint_as_float(o[q4 * 8 + 7]))));
+        }
+      } else {
+#pragma unroll
+        for (int c32 = 0; c32 < 2; ++c32) {
+          if (c32 * 32 >= hcn) break;
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(tDP + lane_addr + hc0 + c32 * 32, o);
+          tmem_wait_ld();
+          if (hf && c32 == 0) mbar_wait(dk_done, phs);   // half 1 stages into the dS buffer, which the dK MMA is still reading
+          uint8_t* orow = stage + c32 * 16384 + r * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4)
+            sts_v4(orow + ((q4 ^ (r & 7)) << 4), make_uint4(o[q4 * 4], o[q4 * 4 + 1], o[q4 * 4 + 2], o[q4 * 4 + 3]));
+        }
       }
       tc_fence_before_sync();
       mbar_arrive(dq_drained);
       fence_proxy_async_smem();
       named_bar_sync(2, 256);
       if (etid == 0) {
+        if (dq16) {
+          tma_reduce_add_2d(&tmDQKV, smP, colQ, qrow0);
+          tma_reduce_add_2d(&tmDQKV, smDS, colQ + 64, qrow0);
+        } else {
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh)
+          for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-          for (int c32 = 0; c32 < 2; ++c32)
-            if (c32 * 32 < (hh ? HD - SPLIT : SPLIT))
-              tma_reduce_add_2d(&tmDQacc, (hh == 0 ? smP : smDS) + c32 * 16384, colQ + (hh ? SPLIT : 0) + c32 * 32, qrow0);
+            for (int c32 = 0; c32 < 2; ++c32)
+              if (c32 * 32 < (hh ? HD - SPLIT : SPLIT))
+                tma_reduce_add_2d(&tmDQacc, (hh == 0 ? smP : smDS) + c32 * 16384, colQ + (hh ? SPLIT : 0) + c32 * 32, qrow0);
+        }
         tma_commit_group();
       }
       if (p.dbg != nullptr && etid == 0) {
@@ -1304,19 +1084,7 @@ int ztb_make_tmap_2d(CUtensorMap* tm, const void* ptr, int elem_bytes, long long
 static int ztb_attn_variant() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("ZTB_ATTN_FWD"); v = e ? atoi(e) : 3; }
-  return v;  // 1 = one CTA/SM (column-split softmax), 2 = two-tile ping-pong, 3 = two CTAs/SM (64-key blocks)
-}
-
-static int launch_fwd2(const CUtensorMap& tq, const CUtensorMap& to, const AttnParams& p, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    ZTB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
-    configured = true;
-  }
-  dim3 grid(p.T / 256, p.B * p.H);
-  attn_fwd2_kernel<<<grid, ATT2_THREADS, Attn2Smem::TOTAL, st>>>(tq, to, p);
-  ZTB_CUDA_CHECK(cudaGetLastError());
-  return 0;
+  return v;  // 1 = one CTA/SM (column-split softmax; the kernel head_dim 64 / 96 always use), 3 = two CTAs/SM (64-key blocks; head_dim 128 default)
 }
 
 template <int HD>
@@ -1371,7 +1139,6 @@ int ztb_attn_fwd(const void* qkv, void* out, float* lse, const float* slopes, in
     ZTB_CUDA_CHECK(cudaGetLastError());
     return 0;
   }
-  if (hd == 128 && T % 256 == 0 && ztb_attn_variant() == 2) return launch_fwd2(tq, to, p, st);
   return hd == 128 ? launch_fwd<128>(tq, to, p, st) : hd == 96 ? launch_fwd<96>(tq, to, p, st) : launch_fwd<64>(tq, to, p, st);
 }
 
@@ -1391,8 +1158,8 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const CUten
   return 0;
 }
 
-// dqkv: [B*T, 3*D] bf16 (written in full); dq_acc: [B*T, D] fp32 scratch, must be zero on entry;
-// delta: [B,H,T] fp32 scratch.
+// dqkv: [B*T, 3*D] bf16 (written in full); dq_acc: [B*T, D] fp32 scratch, must be zero on entry -- or nullptr with
+// head_dim 128: dQ is then accumulated directly in dqkv in bf16 (see AttnBwdParams::dq_bf16); delta: [B,H,T] fp32 scratch.
 int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dq_acc, float* delta,
                  const float* slopes, int B, int T, int H, int hd, float scale, float dropout_p, const uint64_t* rng,
                  uint32_t op_id, int sms, cudaStream_t st, unsigned long long* dbg) {
@@ -1417,8 +1184,12 @@ int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float
   if (rc) return rc;
   rc = ztb_make_tmap_2d(&tdqkv, dqkv, 2, rows, 3 * D, 3 * D, 64, 128);
   if (rc) return rc;
-  rc = ztb_make_tmap_2d(&tacc, dq_acc, 4, rows, D, D, 32, 128);
-  if (rc) return rc;
+  if (dq_acc != nullptr) {
+    rc = ztb_make_tmap_2d(&tacc, dq_acc, 4, rows, D, D, 32, 128);
+    if (rc) return rc;
+  } else {
+    tacc = tdqkv;   // unused by the kernel in bf16-dQ mode
+  }
   AttnBwdParams p;
   p.B = B; p.T = T; p.H = H;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
@@ -1430,8 +1201,13 @@ int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float
   p.rng = rng; p.op_id = op_id;
   p.dqkv = (bf16*)dqkv;
   p.dbg = dbg;
+  p.dq_bf16 = (hd == 128 && dq_acc == nullptr) ? 1 : 0;
+  if (p.dq_bf16)   // the Q columns of dqkv are the reduce-add target: zero them (strided region: a 2-D memset, not a kernel)
+    ZTB_CUDA_CHECK(cudaMemset2DAsync(dqkv, (size_t)3 * D * 2, 0, (size_t)D * 2, (size_t)rows, st));
+  else if (dq_acc == nullptr) { ztb_set_error("ztb_attn_bwd", "dq_acc scratch is required unless head_dim == 128 (bf16 dQ accumulation)", __FILE__, __LINE__); return -1; }
   rc = hd == 128 ? launch_bwd<128>(tq, tdo, tdqkv, tacc, p, st) : hd == 96 ? launch_bwd<96>(tq, tdo, tdqkv, tacc, p, st) : launch_bwd<64>(tq, tdo, tdqkv, tacc, p, st);
   if (rc) return rc;
+  if (p.dq_bf16) return 0;   // dQ is already in dqkv
   size_t n = (size_t)rows * (D / 8);
   size_t g = (n + 255) / 256;
   if (g > (size_t)sms * 8) g = (size_t)sms * 8;

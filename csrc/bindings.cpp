@@ -276,17 +276,19 @@ std::vector<at::Tensor> attention_fwd(const at::Tensor& qkv, const c10::optional
 
 at::Tensor attention_bwd(const at::Tensor& qkv, const at::Tensor& out, const at::Tensor& dout, const at::Tensor& lse,
                          const c10::optional<at::Tensor>& slopes, int64_t H, double scale, double p,
-                         const c10::optional<at::Tensor>& rng, int64_t op_id, const c10::optional<at::Tensor>& dbg) {
+                         const c10::optional<at::Tensor>& rng, int64_t op_id, const c10::optional<at::Tensor>& dbg, bool dq_bf16) {
   need(is_bf16_cuda(qkv) && qkv.dim() == 3 && qkv.is_contiguous() && is_bf16_cuda(out) && out.is_contiguous() && is_bf16_cuda(dout) && dout.is_contiguous(),
        "attention_bwd: bf16 contiguous tensors");
   c10::cuda::CUDAGuard g(qkv.device());
   int B = qkv.size(0), T = qkv.size(1), D = qkv.size(2) / 3, hd = D / H;
   auto dqkv = at::empty_like(qkv);
-  auto acc = at::zeros({(int64_t)B * T, D}, qkv.options().dtype(at::kFloat));
+  const bool dq16 = dq_bf16 && hd == 128;
+  at::Tensor acc;
+  if (!dq16) acc = at::zeros({(int64_t)B * T, D}, qkv.options().dtype(at::kFloat));
   auto delta = at::empty({B, (int)H, T}, qkv.options().dtype(at::kFloat));
   const float* sl = slopes.has_value() ? slopes->data_ptr<float>() : nullptr;
   const uint64_t* r = rng.has_value() ? (const uint64_t*)rng->data_ptr<int64_t>() : nullptr;
-  check(ztb_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr<float>(), dqkv.data_ptr(), acc.data_ptr<float>(),
+  check(ztb_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr<float>(), dqkv.data_ptr(), dq16 ? nullptr : acc.data_ptr<float>(),
                      delta.data_ptr<float>(), sl, B, T, (int)H, hd, (float)scale, (float)p, r, (uint32_t)op_id, num_sms(), stream(),
                      dbg.has_value() ? reinterpret_cast<unsigned long long*>(dbg->data_ptr<int64_t>()) : nullptr), "attention_bwd");
   return dqkv;
@@ -359,7 +361,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("segment_struct_size", &segment_struct_size);
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_bwd", &attention_bwd, py::arg("qkv"), py::arg("out"), py::arg("dout"), py::arg("lse"), py::arg("slopes"), py::arg("H"),
-        py::arg("scale"), py::arg("p"), py::arg("rng"), py::arg("op_id"), py::arg("dbg") = py::none());
+        py::arg("scale"), py::arg("p"), py::arg("rng"), py::arg("op_id"), py::arg("dbg") = py::none(), py::arg("dq_bf16") = false);
   m.def("signal", &signal);
   m.def("wait_flags", &wait_flags);
   m.def("allgather_pull", &allgather_pull);

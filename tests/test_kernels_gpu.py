@@ -469,3 +469,28 @@ def test_embedding_bwd_sorted_handles_frequent_tokens(K, gdtype):
     old = torch.zeros(V, D, device="cuda", dtype=torch.bfloat16)
     K._C.embedding_bwd_(idx, dout, old)
     assert (old.float()[3] - ref[3]).norm() > 5 * (outs[0].float()[3] - ref[3]).norm() or gdtype == torch.float32
+
+
+@pytest.mark.parametrize("B,T,H", [(1, 128, 1), (2, 512, 2), (1, 1024, 2)])
+def test_attention_bwd_bf16_dq_accumulation(K, B, T, H):
+    """head_dim 128 option: dQ partial sums meet in the bf16 dqkv buffer (no fp32 scratch / convert pass).  dK and dV must
+    be bit-identical to the fp32-scratch path; dQ differs only by the per-key-block bf16 rounding."""
+    from zero_transformer_b200.ops.reference import get_slopes
+
+    hd = 128
+    qkv = _rand(B, T, 3 * H * hd)
+    slopes = torch.tensor(get_slopes(H), device="cuda")
+    scale = hd ** -0.5
+    out, lse = K._C.attention_fwd(qkv, slopes, H, scale, 0.0, None, 0)
+    dout = _rand(B, T, H * hd)
+    g32 = K._C.attention_bwd(qkv, out, dout, lse, slopes, H, scale, 0.0, None, 0, dq_bf16=False)
+    g16 = K._C.attention_bwd(qkv, out, dout, lse, slopes, H, scale, 0.0, None, 0, dq_bf16=True)
+    D = H * hd
+    assert torch.equal(g32[..., D:], g16[..., D:])
+    rel = (g32[..., :D].float() - g16[..., :D].float()).norm() / g32[..., :D].float().norm()
+    assert rel < (1e-6 if T == 128 else 8e-3), rel.item()
+    q2 = qkv.detach().float().requires_grad_(True)
+    ro, _ = _attn_ref(q2, slopes, H, scale)
+    ro.backward(dout.float())
+    relr = (g16[..., :D].float() - q2.grad[..., :D]).norm() / q2.grad[..., :D].norm()
+    assert relr < 2e-2, relr.item()

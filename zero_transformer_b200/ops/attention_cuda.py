@@ -33,7 +33,8 @@ class _Attention(torch.autograd.Function):
         qkv, out, lse = ctx.saved_tensors
         sl, n_head, scale, p, op_id = ctx.meta
         rng = K.rng_state(qkv.device)
-        dqkv = K._C.attention_bwd(qkv, out, dout.contiguous(), lse, sl, n_head, scale, p, rng if p > 0 else None, op_id)
+        dqkv = K._C.attention_bwd(qkv, out, dout.contiguous(), lse, sl, n_head, scale, p, rng if p > 0 else None, op_id,
+                                  dq_bf16=K.CONFIG.attn_dq_bf16)
         return dqkv, None, None, None, None
 
 

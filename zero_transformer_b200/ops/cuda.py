@@ -77,6 +77,8 @@ class _Config:
     fuse_wgrad = os.environ.get("ZTB_FUSE_WGRAD", "1") == "1"    # accumulate dW into param.grad in the epilogue
     gemm_2cta = os.environ.get("ZTB_GEMM_2CTA", "1") == "1"      # cta_group::2 256x256 kernel for the big GEMMs
     attn_impl = os.environ.get("ZTB_ATTN", "auto")                # auto | tc (own kernel) | flash (flash_attn library) | ref
+    # head_dim 128: accumulate dQ over key blocks directly in the bf16 dqkv buffer (no fp32 scratch, zero-fill, convert pass)
+    attn_dq_bf16 = os.environ.get("ZTB_ATTN_DQ_BF16", "0") == "1"
     # order-fixed reductions where the fast path uses atomics (LayerNorm weight gradient): bitwise run-to-run
     # reproducibility for T <= 256 (longer sequences: attention dQ has > 2 reduce-add contributions per element)
     deterministic = os.environ.get("ZTB_DETERMINISTIC", "0") == "1"
