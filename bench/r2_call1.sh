@@ -10,5 +10,7 @@ ZTB_UPDATE_MODE=wide timeout 600 python bench.py --steps 6 --warmup 3 2>gpurun_o
 cat gpurun_out/r2_bench_wide.json
 timeout 600 python bench.py --steps 6 --warmup 3 2>gpurun_out/r2_bench_bg.err | tail -1 > gpurun_out/r2_bench_bg.json
 cat gpurun_out/r2_bench_bg.json
+ZTB_ATTN_DQ_BF16=1 timeout 600 python bench.py --steps 6 --warmup 3 2>gpurun_out/r2_bench_dq16.err | tail -1 > gpurun_out/r2_bench_dq16.json
+cat gpurun_out/r2_bench_dq16.json
 timeout 600 python bench/gap_analysis.py > gpurun_out/r2_gap.txt 2>&1
 tail -n 34 gpurun_out/r2_gap.txt
