@@ -12,5 +12,8 @@ timeout 600 python bench.py --steps 6 --warmup 3 2>gpurun_out/r2_bench_bg.err | 
 cat gpurun_out/r2_bench_bg.json
 ZTB_ATTN_DQ_BF16=1 timeout 600 python bench.py --steps 6 --warmup 3 2>gpurun_out/r2_bench_dq16.err | tail -1 > gpurun_out/r2_bench_dq16.json
 cat gpurun_out/r2_bench_dq16.json
+ZTB_PDL=1 timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_model_gpu.py -x -q -m gpu -k "not resume and not train_cli" > gpurun_out/r2_tests_pdl.log 2>&1; echo "pdl tests rc=$?" >> gpurun_out/r2_tests_pdl.log; tail -n 3 gpurun_out/r2_tests_pdl.log
+ZTB_PDL=1 timeout 600 python bench.py --steps 6 --warmup 3 2>gpurun_out/r2_bench_pdl.err | tail -1 > gpurun_out/r2_bench_pdl.json
+cat gpurun_out/r2_bench_pdl.json
 timeout 600 python bench/gap_analysis.py > gpurun_out/r2_gap.txt 2>&1
 tail -n 34 gpurun_out/r2_gap.txt

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "launch.cuh"
 #include "launchers.h"
 
 namespace ztb {
@@ -118,6 +119,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_enter();   // prologue above overlapped the previous kernel's tail; global memory is first touched below
   const uint32_t tS = tmem_base;          // 2 x 128 columns
   const uint32_t tO = tmem_base + 256;    // HD columns
 
@@ -400,6 +402,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_enter();   // prologue above overlapped the previous kernel's tail; global memory is first touched below
   const uint32_t tS = tmem_base;          // 2 x 64 columns
   const uint32_t tO = tmem_base + 128;    // 128 columns
 
@@ -677,6 +680,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_enter();   // prologue above overlapped the previous kernel's tail; global memory is first touched below
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 384;
 
   if (warp == 0) {
@@ -1027,6 +1031,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 template <int HD>
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout,
                                                          float* __restrict__ delta, int B, int T, int H) {
+  pdl_enter();
   constexpr int LPR = HD / 8;                       // lanes per row: 8, 12 or 16
   constexpr int RPW = 32 / LPR;                     // rows per warp pass: 4, 2, 2
   const int lane = threadIdx.x & 31;
@@ -1065,6 +1070,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
 
 // dqkv[:, 0:D] = bf16(dq_acc)
 __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dqkv, size_t rows, int D8) {
+  pdl_enter();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < rows * D8; i += (size_t)gridDim.x * blockDim.x) {
     size_t rrow = i / D8;
     int c = (int)(i % D8);
@@ -1096,8 +1102,7 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& to, const AttnPa
     configured = true;
   }
   dim3 grid(p.T / ATT_BM, p.B * p.H);
-  kern<<<grid, ATT_THREADS, AttnSmem<HD>::TOTAL, st>>>(tq, to, p);
-  ZTB_CUDA_CHECK(cudaGetLastError());
+  ZTB_CUDA_CHECK(ztb_launch(kern, grid, dim3(ATT_THREADS), AttnSmem<HD>::TOTAL, st, tq, to, p));
   return 0;
 }
 
@@ -1135,8 +1140,7 @@ int ztb_attn_fwd(const void* qkv, void* out, float* lse, const float* slopes, in
       configured = true;
     }
     dim3 grid(T / ATT_BM, B * H);
-    attn_fwd3_kernel<<<grid, ATT3_THREADS, Attn3Smem::TOTAL, st>>>(tq, tkv, to, p);
-    ZTB_CUDA_CHECK(cudaGetLastError());
+    ZTB_CUDA_CHECK(ztb_launch(attn_fwd3_kernel, grid, dim3(ATT3_THREADS), Attn3Smem::TOTAL, st, tq, tkv, to, p));
     return 0;
   }
   return hd == 128 ? launch_fwd<128>(tq, to, p, st) : hd == 96 ? launch_fwd<96>(tq, to, p, st) : launch_fwd<64>(tq, to, p, st);
@@ -1153,8 +1157,7 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const CUten
     configured = true;
   }
   dim3 grid(p.T / ATT_BN, p.B * p.H);
-  kern<<<grid, ATT_THREADS, AttnBwdSmem<HD>::TOTAL, st>>>(tq, tdo, tdqkv, tacc, p);
-  ZTB_CUDA_CHECK(cudaGetLastError());
+  ZTB_CUDA_CHECK(ztb_launch(kern, grid, dim3(ATT_THREADS), AttnBwdSmem<HD>::TOTAL, st, tq, tdo, tdqkv, tacc, p));
   return 0;
 }
 
@@ -1172,11 +1175,9 @@ int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float
     const long long nr = rows * H;
     const int rpw = 32 / (hd / 8);
     const unsigned blocks = (unsigned)((nr + 8 * rpw - 1) / (8 * rpw));
-    if (hd == 128) attn_delta_kernel<128><<<blocks, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, T, H);
-    else if (hd == 96) attn_delta_kernel<96><<<blocks, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, T, H);
-    else attn_delta_kernel<64><<<blocks, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, T, H);
+    auto kd = hd == 128 ? attn_delta_kernel<128> : hd == 96 ? attn_delta_kernel<96> : attn_delta_kernel<64>;
+    ZTB_CUDA_CHECK(ztb_launch(kd, dim3(blocks), dim3(256), 0, st, (const bf16*)out, (const bf16*)dout, delta, B, T, H));
   }
-  ZTB_CUDA_CHECK(cudaGetLastError());
   CUtensorMap tq, tdo, tdqkv, tacc;
   int rc = ztb_make_tmap_2d(&tq, qkv, 2, rows, 3 * D, 3 * D, 64, 128);
   if (rc) return rc;
@@ -1211,7 +1212,6 @@ int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float
   size_t n = (size_t)rows * (D / 8);
   size_t g = (n + 255) / 256;
   if (g > (size_t)sms * 8) g = (size_t)sms * 8;
-  attn_dq_convert_kernel<<<(unsigned)g, 256, 0, st>>>(dq_acc, (bf16*)dqkv, (size_t)rows, (int)(D / 8));
-  ZTB_CUDA_CHECK(cudaGetLastError());
+  ZTB_CUDA_CHECK(ztb_launch(attn_dq_convert_kernel, dim3((unsigned)g), dim3(256), 0, st, (const float*)dq_acc, (bf16*)dqkv, (size_t)rows, (int)(D / 8)));
   return 0;
 }

@@ -5,6 +5,7 @@
 // src/models/GPT.py:75-83, bias-free LayerNorm GPT.py:42,49,98, dropout + residual layers.py:77,191 and
 // GPT.py:43-49, tanh-GELU layers.py:68, shifted cross entropy GPT.py:105-111 + src/utils/losses.py:9-23.
 #include "common.cuh"
+#include "launch.cuh"
 #include "launchers.h"
 
 namespace ztb {
@@ -20,6 +21,7 @@ template <int NV>
 __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                             bf16* __restrict__ y, float* __restrict__ mean,
                                                             float* __restrict__ rstd, int M, float eps) {
+  pdl_enter();
   constexpr int D = NV * 256;
   int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
                                                             const float* __restrict__ rstd, bf16* __restrict__ dx,
                                                             float* __restrict__ dw, int M, const bf16* __restrict__ dres,
                                                             const LnBwdExtra ex) {
+  pdl_enter();
   constexpr int D = NV * 256;
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float acc[NV * 8];
@@ -254,6 +257,7 @@ template <bool kHasRes>
 __global__ void __launch_bounds__(256) dropout_add_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res,
                                                           bf16* __restrict__ out, size_t n8, float p, float inv_keep,
                                                           const uint64_t* __restrict__ rng, uint32_t op_id) {
+  pdl_enter();
   uint64_t seed = rng[0], stream = rng[1] * 65536ull + op_id;
   Philox ph(seed);
   uint32_t thr = dropout_threshold(p);
@@ -280,6 +284,7 @@ __global__ void __launch_bounds__(256) dropout_add_kernel(const bf16* __restrict
 // ============================================================== embedding
 __global__ void __launch_bounds__(128) embedding_fwd_kernel(const int* __restrict__ idx, const bf16* __restrict__ wte,
                                                             bf16* __restrict__ out, int M, int D8, int V) {
+  pdl_enter();
   int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= M) return;
   int t = idx[row];
@@ -398,6 +403,7 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const bf16* __restrict__ 
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const bf16* __restrict__ logits, const int* __restrict__ labels,
                                                      float* __restrict__ lse, float* __restrict__ nll, int V, size_t ld) {
   __shared__ float shm[8], shs[8];
+  pdl_enter();
   int row = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bf16* lr = logits + (size_t)row * ld;
   float mx = -INFINITY, sm = 0.f;
@@ -441,6 +447,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const bf16* __restrict__ lo
 __global__ void __launch_bounds__(256) ce_bwd_kernel(bf16* __restrict__ logits, const int* __restrict__ labels,
                                                      const float* __restrict__ lse, const float* __restrict__ gscale,
                                                      float inv_count, int V, size_t ld) {
+  pdl_enter();
   int row = blockIdx.x;
   bf16* lr = logits + (size_t)row * ld;
   int lab = labels[row];
@@ -478,12 +485,12 @@ static int grid_for(size_t n, int block, int max_blocks) {
 
 #define LN_DISPATCH(NV, KERNEL, GRID, ...)                                                     \
   switch (NV) {                                                                                \
-    case 1: KERNEL<1><<<GRID, 128, 0, st>>>(__VA_ARGS__); break;                               \
-    case 2: KERNEL<2><<<GRID, 128, 0, st>>>(__VA_ARGS__); break;                               \
-    case 3: KERNEL<3><<<GRID, 128, 0, st>>>(__VA_ARGS__); break;                               \
-    case 4: KERNEL<4><<<GRID, 128, 0, st>>>(__VA_ARGS__); break;                               \
-    case 6: KERNEL<6><<<GRID, 128, 0, st>>>(__VA_ARGS__); break;                               \
-    case 8: KERNEL<8><<<GRID, 128, 0, st>>>(__VA_ARGS__); break;                               \
+    case 1: ztb_launch(KERNEL<1>, dim3(GRID), dim3(128), 0, st, __VA_ARGS__); break;           \
+    case 2: ztb_launch(KERNEL<2>, dim3(GRID), dim3(128), 0, st, __VA_ARGS__); break;           \
+    case 3: ztb_launch(KERNEL<3>, dim3(GRID), dim3(128), 0, st, __VA_ARGS__); break;           \
+    case 4: ztb_launch(KERNEL<4>, dim3(GRID), dim3(128), 0, st, __VA_ARGS__); break;           \
+    case 6: ztb_launch(KERNEL<6>, dim3(GRID), dim3(128), 0, st, __VA_ARGS__); break;           \
+    case 8: ztb_launch(KERNEL<8>, dim3(GRID), dim3(128), 0, st, __VA_ARGS__); break;           \
   }
 
 static bool ln_fast(int D) {
@@ -531,15 +538,15 @@ int ztb_dropout_add(const void* y, const void* res, void* out, size_t n, float p
   int grid = grid_for(n8, 256, sms * 8);
   float inv_keep = p < 1.f ? 1.f / (1.f - p) : 0.f;
   if (res)
-    dropout_add_kernel<true><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)res, (bf16*)out, n8, p, inv_keep, rng, op_id);
+    ztb_launch(dropout_add_kernel<true>, dim3(grid), dim3(256), 0, st, (const bf16*)y, (const bf16*)res, (bf16*)out, n8, p, inv_keep, rng, op_id);
   else
-    dropout_add_kernel<false><<<grid, 256, 0, st>>>((const bf16*)y, nullptr, (bf16*)out, n8, p, inv_keep, rng, op_id);
+    ztb_launch(dropout_add_kernel<false>, dim3(grid), dim3(256), 0, st, (const bf16*)y, (const bf16*)nullptr, (bf16*)out, n8, p, inv_keep, rng, op_id);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 int ztb_embedding_fwd(const int* idx, const void* wte, void* out, int M, int D, int V, cudaStream_t st) {
-  embedding_fwd_kernel<<<(M + 3) / 4, 128, 0, st>>>(idx, (const bf16*)wte, (bf16*)out, M, D / 8, V);
+  ztb_launch(embedding_fwd_kernel, dim3((M + 3) / 4), dim3(128), 0, st, idx, (const bf16*)wte, (bf16*)out, M, D / 8, V);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -574,13 +581,13 @@ int ztb_gelu_fwd(const void* z, void* g, size_t n, int sms, cudaStream_t st) {
 }
 
 int ztb_ce_fwd(const void* logits, const int* labels, float* lse, float* nll, int M, int V, size_t ld, cudaStream_t st) {
-  ce_fwd_kernel<<<M, 256, 0, st>>>((const bf16*)logits, labels, lse, nll, V, ld);
+  ztb_launch(ce_fwd_kernel, dim3(M), dim3(256), 0, st, (const bf16*)logits, labels, lse, nll, V, ld);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 int ztb_ce_bwd(void* logits, const int* labels, const float* lse, const float* gscale, float inv_count, int M, int V,
                size_t ld, cudaStream_t st) {
-  ce_bwd_kernel<<<M, 256, 0, st>>>((bf16*)logits, labels, lse, gscale, inv_count, V, ld);
+  ztb_launch(ce_bwd_kernel, dim3(M), dim3(256), 0, st, (bf16*)logits, labels, lse, gscale, inv_count, V, ld);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

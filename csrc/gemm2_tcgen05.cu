@@ -14,6 +14,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "launch.cuh"
 #include "launchers.h"
 
 namespace ztb {
@@ -232,6 +233,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_enter();   // everything above overlapped the previous kernel's tail; no global memory has been touched yet
 
   // Control warps take the HIGHEST warp ids: the SMSP arbiter favours high warp ids, so the TMA
   // producer and the MMA issuer are never starved by the ALU-heavy epilogue warps (0-7).
@@ -585,8 +587,7 @@ static int launch2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap
   }
   g2::AgParams ag{};
   if (agp) ag = *agp;
-  kern<<<grid, g2::GEMM_THREADS, g2::GEMM_SMEM, st>>>(a, b, c, x, p, ag);  // cluster dims are compile-time (2,1,1)
-  ZTB_CUDA_CHECK(cudaGetLastError());
+  ZTB_CUDA_CHECK(ztb_launch(kern, dim3(grid), dim3(g2::GEMM_THREADS), g2::GEMM_SMEM, st, a, b, c, x, p, ag));  // cluster dims are compile-time (2,1,1)
   return 0;
 }
 

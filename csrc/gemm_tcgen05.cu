@@ -18,6 +18,7 @@
 #include <stdio.h>
 
 #include "common.cuh"
+#include "launch.cuh"
 #include "launchers.h"
 
 namespace ztb {
@@ -127,6 +128,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_enter();
 
   // Control warps take the highest warp ids (the SMSP arbiter favours them over the epilogue warps).
   if (warp == 4) {
@@ -431,8 +433,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
     ZTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
     configured = true;
   }
-  kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, b, c, x, p, ag);
-  ZTB_CUDA_CHECK(cudaGetLastError());
+  ZTB_CUDA_CHECK(ztb_launch(kern, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM, st, a, b, c, x, p, ag));
   return 0;
 }
 

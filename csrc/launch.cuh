@@ -1,0 +1,39 @@
+// Kernel launch helper with programmatic dependent launch (PDL).
+//
+// Every kernel of the training step is launched with cudaLaunchAttributeProgrammaticStreamSerialization: the grid may be
+// scheduled while its predecessor in the stream is still draining, runs its prologue (barrier init, TMEM allocation,
+// tensor-map prefetch, index math), and blocks in `griddepcontrol.wait` until the predecessor has completed and its
+// memory is visible -- that hides the ~2.5 us launch latency that otherwise sits between two dependent kernels
+// (~1100 launches per 1.3B step).  A kernel lets ITS successor start early with `griddepcontrol.launch_dependents`.
+// Rules every participating kernel follows: no global-memory access before pdl_wait(); pdl_wait() is executed by every
+// thread that later touches global memory.  Kernels launched without the attribute (torch's own, the communication
+// stream's) are unaffected: for them both instructions are no-ops / the dependency stays a full stream dependency.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdlib.h>
+
+#include <utility>
+
+inline bool ztb_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ZTB_PDL"); v = e ? (atoi(e) != 0) : 0;   // opt-in until the A/B run (bench/r2_call1.sh) has shown the gain on the target box }
+  return v != 0;
+}
+
+template <typename... P, typename... A>
+inline cudaError_t ztb_launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = ztb_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(std::forward<A>(args))...);
+}
+
+#ifdef __CUDACC__
+// wait for the predecessor grid (complete + memory visible); then allow the successor to be scheduled
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_launch_dependents(); }
+#endif
