@@ -16,7 +16,10 @@
 
 inline bool ztb_pdl_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("ZTB_PDL"); v = e ? (atoi(e) != 0) : 0;   // opt-in until the A/B run (bench/r2_call1.sh) has shown the gain on the target box }
+  if (v < 0) {
+    const char* e = getenv("ZTB_PDL");
+    v = e ? (atoi(e) != 0) : 0;   // opt-in until the A/B run (bench/r2_call1.sh) has shown the gain on the target box
+  }
   return v != 0;
 }
 
