@@ -72,7 +72,7 @@ ZTB_DEVINL void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
 
 // 16 keep/drop decisions for elements [16*g, 16*g+16) of row `row_id` from one Philox call
 ZTB_DEVINL uint4 attn_dropout_bits(const Philox& ph, uint64_t row_id, uint32_t g, uint64_t stream) {
-  return ph.rounds<6>(row_id * 4096ull + g, stream);
+  return ph.rounds<kPhiloxRounds>(row_id * 4096ull + g, stream);
 }
 
 template <int HD>

@@ -77,15 +77,18 @@ ZTB_DEVINL float gelu_tanh_grad(float x) {
   return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * du;
 }
 
-// ------------------------------------------------------------------ Philox4x32-10
+// ------------------------------------------------------------------ Philox4x32
+// Dropout masks use the 7-round variant: Philox4x32-7 is the smallest round count Random123 documents as
+// Crush-resistant (10 is its conservative default); one call per 16 attention probabilities sits in the softmax
+// critical path, so the rounds are not free.  Every mask site (GEMM epilogue, dropout_add, LayerNorm-backward mask,
+// attention forward / backward) uses the same constant, so a mask regenerated in backward is the forward's mask.
+constexpr int kPhiloxRounds = 7;
 // Counter-based RNG: dropout masks are regenerated in backward from (seed, offset)
 // instead of being stored (per (step, rank, micro-step, layer, op) streams).
 struct Philox {
   uint32_t k0, k1;
   ZTB_DEVINL Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
   ZTB_DEVINL uint4 operator()(uint64_t ctr, uint64_t stream) const { return rounds<10>(ctr, stream); }
-  // reduced-round variant for the attention-probability mask (one call per 16 elements inside the
-  // softmax critical path); 6 rounds decorrelate dropout decisions more than adequately
   template <int R>
   ZTB_DEVINL uint4 rounds(uint64_t ctr, uint64_t stream) const {
     uint4 c = make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)stream, (uint32_t)(stream >> 32));

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
       st_v4(dr + i * 32 + lane, make_uint4(os[0], os[1], os[2], os[3]));
       if (drop) {  // masked copy of the (bf16-rounded) dx, exactly what dropout_add_kernel<false> would produce from it
         const size_t vi = (size_t)row * (D / 8) + i * 32 + lane;
-        uint4 r0 = ph.rounds<6>(2 * vi, stream), r1 = ph.rounds<6>(2 * vi + 1, stream);
+        uint4 r0 = ph.rounds<kPhiloxRounds>(2 * vi, stream), r1 = ph.rounds<kPhiloxRounds>(2 * vi + 1, stream);
         uint32_t rb[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w}, ms[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -241,7 +241,7 @@ __global__ void layernorm_bwd_generic(const bf16* __restrict__ dy, const bf16* _
     if (ex.dmask != nullptr) {   // same mask as dropout_add_kernel: element e -> Philox counter e / 4, word e % 4
       const size_t e = (size_t)row * D + c;
       Philox ph(ex.rng[0]);
-      uint4 r4 = ph.rounds<6>(e >> 2, ex.rng[1] * 65536ull + ex.op_id);
+      uint4 r4 = ph.rounds<kPhiloxRounds>(e >> 2, ex.rng[1] * 65536ull + ex.op_id);
       uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
       ex.dmask[e] = __float2bfloat16(rw[e & 3] >= dropout_threshold(ex.p) ? __bfloat162float(o) * ex.inv_keep : 0.f);
     }
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256) dropout_add_kernel(const bf16* __restrict
   uint32_t thr = dropout_threshold(p);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
     uint4 uy = ld_nc_v4(reinterpret_cast<const uint4*>(y) + i);
-    uint4 r0 = ph.rounds<6>(2 * i, stream), r1 = ph.rounds<6>(2 * i + 1, stream);
+    uint4 r0 = ph.rounds<kPhiloxRounds>(2 * i, stream), r1 = ph.rounds<kPhiloxRounds>(2 * i + 1, stream);
     uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
     uint32_t ys[4] = {uy.x, uy.y, uy.z, uy.w};
     uint32_t rs[4] = {0, 0, 0, 0};

@@ -500,7 +500,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               uint32_t us[4] = {au[q].x, au[q].y, au[q].z, au[q].w};
               if constexpr (EPI == ZTB_EPI_DROPOUT_ADD) {
                 size_t idx = (size_t)grow * p.N + hcol + q * 8;
-                uint4 r0 = ph.rounds<6>(idx >> 2, stream), r1 = ph.rounds<6>((idx >> 2) + 1, stream);
+                uint4 r0 = ph.rounds<kPhiloxRounds>(idx >> 2, stream), r1 = ph.rounds<kPhiloxRounds>((idx >> 2) + 1, stream);
                 uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {

@@ -328,7 +328,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint32_t us[4] = {u.x, u.y, u.z, u.w};
             if (p.epi == ZTB_EPI_DROPOUT_ADD) {
               size_t idx = (size_t)grow * p.N + gcol + q * 8;
-              uint4 r0 = ph.rounds<6>(idx >> 2, stream), r1 = ph.rounds<6>((idx >> 2) + 1, stream);
+              uint4 r0 = ph.rounds<kPhiloxRounds>(idx >> 2, stream), r1 = ph.rounds<kPhiloxRounds>((idx >> 2) + 1, stream);
               uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
