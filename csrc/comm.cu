@@ -143,7 +143,21 @@ __global__ void __launch_bounds__(256) p2p_copy_kernel(uint4* __restrict__ dst, 
 
 using namespace ztb;
 
+// The flag kernels can be resident for a long time (a wait spins until the slowest peer arrives) on an SM that the
+// backward pass needs for a 225 KB tcgen05 CTA, and an SM cannot change its L1 / shared split while a CTA is resident:
+// make them prefer the maximum shared-memory carveout so they never pin an SM in an incompatible configuration.
+static void prefer_max_carveout_once() {
+  static bool done = false;
+  if (done) return;
+  cudaFuncSetAttribute(wait_flags_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(signal_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(allgather_pull_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(reduce_scatter_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  done = true;
+}
+
 int ztb_wait_flags(const int* flags, int n, int value, cudaStream_t st) {
+  prefer_max_carveout_once();
   wait_flags_kernel<<<1, 32, 0, st>>>(flags, n, value);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -153,6 +167,7 @@ int ztb_signal(void* const* pads, int n, int slot, int value, cudaStream_t st) {
   if (n < 1 || n > kMaxRanks) { ztb_set_error("ztb_signal", "bad rank count", __FILE__, __LINE__); return -1; }
   PtrList pl;
   for (int i = 0; i < kMaxRanks; ++i) pl.p[i] = i < n ? pads[i] : nullptr;
+  prefer_max_carveout_once();
   signal_kernel<<<1, 32, 0, st>>>(pl, n, slot, value);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -164,6 +179,7 @@ int ztb_allgather_pull(void* dst, void* const* srcs, int world, const ZtbSegment
   PtrList pl;
   for (int i = 0; i < kMaxRanks; ++i) pl.p[i] = i < world ? srcs[i] : nullptr;
   long long want = total_tiles < (long long)sms * 4 ? total_tiles : (long long)sms * 4;
+  prefer_max_carveout_once();
   allgather_pull_kernel<<<(int)want, kCopyThreads, 0, st>>>((bf16*)dst, pl, segs, nseg, total_tiles, flags, world, wait_value);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -175,6 +191,7 @@ int ztb_reduce_scatter(void* out, void* const* grads, int n_peers, const ZtbSegm
   PtrList pl;
   for (int i = 0; i < kMaxRanks; ++i) pl.p[i] = i < n_peers ? grads[i] : nullptr;
   long long want = total_tiles < (long long)sms * 8 ? total_tiles : (long long)sms * 8;
+  prefer_max_carveout_once();
   reduce_scatter_kernel<<<(int)want, 256, 0, st>>>((bf16*)out, pl, n_peers, segs, nseg, total_tiles, flags, wait_value);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;

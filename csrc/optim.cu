@@ -196,6 +196,17 @@ int ztb_adamw_shard(float* master, float* m, float* v, void* flat_param, const v
   long long units = (total_tiles + unroll - 1) / unroll;
   long long cap = max_ctas > 0 ? (long long)max_ctas : (long long)sms * 16;
   int grid = (int)(units < cap ? units : cap);
+  // Shared-memory carveout: an SM cannot change its L1 / shared split while a CTA is resident.  These CTAs use no shared
+  // memory, so by default they could pin an SM they land on (between two kernels of the backward pass) in a small-shared
+  // configuration for their whole lifetime, and the next 225 KB tcgen05 CTA would have to wait for them.  Preferring the
+  // maximum carveout makes an update CTA always compatible with the GEMM / attention CTAs it is meant to sit next to.
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    cudaFuncSetAttribute(adamw_shard_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(adamw_shard_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(adamw_shard_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carveout_set = true;
+  }
 #define ZTB_ADAM_LAUNCH(FP32, MULTI) adamw_shard_kernel<FP32, MULTI><<<grid, kAdamThreads, 0, st>>>( \
     master, m, v, (bf16*)flat_param, pp, n_peers, segs, nseg, total_tiles, a, wait_flags, wait_value, mc_grad, mc_param)
   if (grad_is_fp32) ZTB_ADAM_LAUNCH(true, false);
