@@ -182,7 +182,10 @@ def main():
         ms = e0.elapsed_time(e1)
         return pdist.max_over_ranks(ms, env.device), last
 
-    for i in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 3)
+    if getattr(tr, "use_graph", False):
+        n_warm = max(n_warm, tr.graph_warmup + 2)   # the eager warm-up steps, the capture itself and one replay stay out of the timed region
+    for i in range(n_warm):
         step_e2e(i)
     counter = getattr(ops._k(), "LAUNCHES", None) if args.impl == "ours" else None
     sampler = ClockSampler(env.local_rank)
@@ -206,7 +209,7 @@ def main():
         pk = measured_peaks()
         rec = {
             "metric": f"tokens/sec (whole box, max over ranks) GPT-2 {MODEL_LABEL.get(MODEL, MODEL)} ZeRO-1", "value": round(tok_s, 1), "unit": "tokens/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev / args.steps, 3),
+            "n_gpus": world, "steps": args.steps, "warmup": n_warm, "cuda_graph": bool(getattr(tr, "use_graph", False)), "ms_per_step": round(ms_dev / args.steps, 3),
             "higher_is_better": True, "scaling": "weak",
             "vs_baseline": (round(tok_s / base["value"], 3) if base and args.impl == "ours" else None),
             "vs_baseline_source": (base["source"] if base and args.impl == "ours" else None),

@@ -209,7 +209,7 @@ at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tens
 // Forward GEMM C = A * B^T with the ZeRO-1 all-gather of B's bucket fused into the kernel.
 at::Tensor gemm_ag(const at::Tensor& A, const at::Tensor& B, std::vector<int64_t> peer_ptrs, at::Tensor& local_flat, const at::Tensor& segs,
                    int64_t nseg, int64_t n_b_segs, int64_t total_tiles, int64_t shard_ready_ptr, int64_t epoch, at::Tensor& done,
-                   int64_t b_tiles_per_rank, int64_t rows_per_rank, int64_t world, int64_t rank, bool two_cta) {
+                   int64_t b_tiles_per_rank, int64_t rows_per_rank, int64_t world, int64_t rank, bool two_cta, int64_t epoch_ptr) {
   need(is_bf16_cuda(A) && is_bf16_cuda(B) && A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "gemm_ag: A, B bf16 2-D");
   need(A.size(1) == B.size(1), "gemm_ag: K mismatch");
   need(done.is_cuda() && done.numel() >= 8 && done.element_size() == 4, "gemm_ag: done must be an 8-element 32-bit CUDA tensor");
@@ -220,7 +220,7 @@ at::Tensor gemm_ag(const at::Tensor& A, const at::Tensor& B, std::vector<int64_t
   for (size_t i = 0; i < peer_ptrs.size() && i < 8; ++i) ag.peer[i] = reinterpret_cast<const void*>(peer_ptrs[i]);
   ag.local = local_flat.data_ptr();
   ag.segs = reinterpret_cast<const ZtbSegment*>(segs.data_ptr()); ag.nseg = (int)nseg; ag.n_b_segs = (int)n_b_segs; ag.total_tiles = total_tiles;
-  ag.shard_ready = reinterpret_cast<const int*>(shard_ready_ptr); ag.epoch = (int)epoch;
+  ag.shard_ready = reinterpret_cast<const int*>(shard_ready_ptr); ag.epoch = (int)epoch; ag.epoch_ptr = reinterpret_cast<const int*>(epoch_ptr);
   ag.done = reinterpret_cast<unsigned int*>(done.data_ptr()); ag.b_tiles_per_rank = (unsigned)b_tiles_per_rank;
   ag.rows_per_rank = (int)rows_per_rank; ag.world = (int)world; ag.rank = (int)rank;
   ZtbGemmArgs a{};
@@ -237,7 +237,8 @@ at::Tensor gemm_ag(const at::Tensor& A, const at::Tensor& B, std::vector<int64_t
 // peer's flat gradient buffer (first = local).  segs: uint8 CUDA tensor of packed ZtbSegment.
 void adamw_shard(at::Tensor& master, at::Tensor& m, at::Tensor& v, at::Tensor& flat_param, std::vector<int64_t> grad_ptrs,
                  bool grad_is_fp32, const at::Tensor& segs, int64_t nseg, int64_t total_tiles, double lr, double beta1, double beta2,
-                 double eps, double wd, double clip, double grad_scale, int64_t step, int64_t wait_flags_ptr, int64_t wait_value, int64_t max_ctas, int64_t scale_mul_ptr, int64_t mc_grad_ptr, int64_t mc_param_ptr) {
+                 double eps, double wd, double clip, double grad_scale, int64_t step, int64_t wait_flags_ptr, int64_t wait_value, int64_t max_ctas, int64_t scale_mul_ptr, int64_t mc_grad_ptr, int64_t mc_param_ptr,
+                 int64_t dyn_ptr) {
   need(master.is_cuda() && master.scalar_type() == at::kFloat && m.scalar_type() == at::kFloat && v.scalar_type() == at::kFloat, "adamw_shard: fp32 state");
   need(is_bf16_cuda(flat_param), "adamw_shard: bf16 flat_param");
   need(segs.is_cuda() && segs.scalar_type() == at::kByte && segs.numel() >= (int64_t)(nseg * sizeof(ZtbSegment)), "adamw_shard: segs");
@@ -248,6 +249,7 @@ void adamw_shard(at::Tensor& master, at::Tensor& m, at::Tensor& v, at::Tensor& f
   a.lr = (float)lr; a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps; a.wd = (float)wd; a.clip = (float)clip;
   a.grad_scale = (float)grad_scale;
   a.scale_mul = reinterpret_cast<const float*>(scale_mul_ptr);
+  a.dyn = reinterpret_cast<const float*>(dyn_ptr);
   a.inv_bc1 = (float)(1.0 / (1.0 - std::pow(beta1, (double)step)));
   a.inv_bc2 = (float)(1.0 / (1.0 - std::pow(beta2, (double)step)));
   a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
@@ -301,13 +303,13 @@ std::vector<void*> to_ptrs(const std::vector<int64_t>& v) {
 }
 
 // release-store `value` into slot `slot` of every listed flag pad (device addresses, peers included)
-void signal(std::vector<int64_t> pad_ptrs, int64_t slot, int64_t value) {
+void signal(std::vector<int64_t> pad_ptrs, int64_t slot, int64_t value, int64_t value_ptr) {
   auto p = to_ptrs(pad_ptrs);
-  check(ztb_signal(p.data(), (int)p.size(), (int)slot, (int)value, stream()), "signal");
+  check(ztb_signal(p.data(), (int)p.size(), (int)slot, (int)value, stream(), reinterpret_cast<const int*>(value_ptr)), "signal");
 }
 
-void wait_flags(int64_t flags_ptr, int64_t n, int64_t value) {
-  check(ztb_wait_flags(reinterpret_cast<const int*>(flags_ptr), (int)n, (int)value, stream()), "wait_flags");
+void wait_flags(int64_t flags_ptr, int64_t n, int64_t value, int64_t value_ptr) {
+  check(ztb_wait_flags(reinterpret_cast<const int*>(flags_ptr), (int)n, (int)value, stream(), reinterpret_cast<const int*>(value_ptr)), "wait_flags");
 }
 
 void allgather_pull(at::Tensor& flat_param, std::vector<int64_t> src_ptrs, const at::Tensor& segs, int64_t nseg, int64_t total_tiles,
@@ -353,17 +355,17 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("direct_store") = -1, py::arg("raster_n") = -1);
   m.def("gemm_ag", &gemm_ag, py::arg("A"), py::arg("B"), py::arg("peer_ptrs"), py::arg("local_flat"), py::arg("segs"), py::arg("nseg"),
         py::arg("n_b_segs"), py::arg("total_tiles"), py::arg("shard_ready_ptr"), py::arg("epoch"), py::arg("done"), py::arg("b_tiles_per_rank"),
-        py::arg("rows_per_rank"), py::arg("world"), py::arg("rank"), py::arg("two_cta") = false);
+        py::arg("rows_per_rank"), py::arg("world"), py::arg("rank"), py::arg("two_cta") = false, py::arg("epoch_ptr") = 0);
   m.def("adamw_shard", &adamw_shard, py::arg("master"), py::arg("m"), py::arg("v"), py::arg("flat_param"), py::arg("grad_ptrs"),
         py::arg("grad_is_fp32"), py::arg("segs"), py::arg("nseg"), py::arg("total_tiles"), py::arg("lr"), py::arg("beta1"), py::arg("beta2"),
         py::arg("eps"), py::arg("wd"), py::arg("clip"), py::arg("grad_scale"), py::arg("step"), py::arg("wait_flags_ptr") = 0,
-        py::arg("wait_value") = 0, py::arg("max_ctas") = 0, py::arg("scale_mul_ptr") = 0, py::arg("mc_grad_ptr") = 0, py::arg("mc_param_ptr") = 0);
+        py::arg("wait_value") = 0, py::arg("max_ctas") = 0, py::arg("scale_mul_ptr") = 0, py::arg("mc_grad_ptr") = 0, py::arg("mc_param_ptr") = 0, py::arg("dyn_ptr") = 0);
   m.def("segment_struct_size", &segment_struct_size);
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_bwd", &attention_bwd, py::arg("qkv"), py::arg("out"), py::arg("dout"), py::arg("lse"), py::arg("slopes"), py::arg("H"),
         py::arg("scale"), py::arg("p"), py::arg("rng"), py::arg("op_id"), py::arg("dbg") = py::none(), py::arg("dq_bf16") = false);
-  m.def("signal", &signal);
-  m.def("wait_flags", &wait_flags);
+  m.def("signal", &signal, py::arg("pad_ptrs"), py::arg("slot"), py::arg("value"), py::arg("value_ptr") = 0);
+  m.def("wait_flags", &wait_flags, py::arg("flags_ptr"), py::arg("n"), py::arg("value"), py::arg("value_ptr") = 0);
   m.def("allgather_pull", &allgather_pull);
   m.def("reduce_scatter", &reduce_scatter);
   m.def("p2p_copy", &p2p_copy);

@@ -50,7 +50,10 @@ ZTB_DEVINL void st_release_sys_i32(int* p, int v) {
 // 1-warp spin-wait on a row of flags.  Cross-rank waits that overlap with compute run here (one
 // tiny CTA) instead of inside the big kernels, so a stalled peer can never pin SM resources that
 // this rank's own backward needs to make progress.
-__global__ void wait_flags_kernel(const int* flags, int n, int value) {
+// `vptr` (optional): the step counter lives on the device (CUDA-graph replays cannot bake a new value into the launch);
+// the awaited / published value is then *vptr + value.
+__global__ void wait_flags_kernel(const int* flags, int n, int value, const int* vptr) {
+  if (vptr != nullptr) value += *vptr;
   if ((int)threadIdx.x < n) {
     const unsigned long long t0 = globaltimer_ns();
     while (ld_acquire_sys_i32(flags + threadIdx.x) < value) {
@@ -64,7 +67,8 @@ __global__ void wait_flags_kernel(const int* flags, int n, int value) {
   }
 }
 
-__global__ void signal_kernel(PtrList pads, int n, int slot, int value) {
+__global__ void signal_kernel(PtrList pads, int n, int slot, int value, const int* vptr) {
+  if (vptr != nullptr) value += *vptr;
   if ((int)threadIdx.x < n) {
     __threadfence_system();
     st_release_sys_i32(reinterpret_cast<int*>(pads.p[threadIdx.x]) + slot, value);
@@ -156,19 +160,19 @@ static void prefer_max_carveout_once() {
   done = true;
 }
 
-int ztb_wait_flags(const int* flags, int n, int value, cudaStream_t st) {
+int ztb_wait_flags(const int* flags, int n, int value, cudaStream_t st, const int* vptr) {
   prefer_max_carveout_once();
-  wait_flags_kernel<<<1, 32, 0, st>>>(flags, n, value);
+  wait_flags_kernel<<<1, 32, 0, st>>>(flags, n, value, vptr);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
-int ztb_signal(void* const* pads, int n, int slot, int value, cudaStream_t st) {
+int ztb_signal(void* const* pads, int n, int slot, int value, cudaStream_t st, const int* vptr) {
   if (n < 1 || n > kMaxRanks) { ztb_set_error("ztb_signal", "bad rank count", __FILE__, __LINE__); return -1; }
   PtrList pl;
   for (int i = 0; i < kMaxRanks; ++i) pl.p[i] = i < n ? pads[i] : nullptr;
   prefer_max_carveout_once();
-  signal_kernel<<<1, 32, 0, st>>>(pl, n, slot, value);
+  signal_kernel<<<1, 32, 0, st>>>(pl, n, slot, value, vptr);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -162,6 +162,7 @@ struct AgParams {
   long long total_tiles;
   const int* shard_ready;       // my flag row: [rank] >= epoch once that rank's chunk is final
   int epoch;
+  const int* epoch_ptr;         // non-null: wait for *epoch_ptr + epoch (device-side step counter, CUDA-graph replays)
   unsigned int* done;           // [8] per-owner count of landed B tiles (zeroed before launch)
   unsigned int b_tiles_per_rank;
   int rows_per_rank;            // B rows owned by each rank
@@ -313,6 +314,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if constexpr (AG) {
       if (lane == 0) {
         unsigned seen = 1u << ag.rank;
+        const int want_epoch = ag.epoch + (ag.epoch_ptr != nullptr ? *ag.epoch_ptr : 0);
         // Ring of AG_SLOTS 8 KB slots.  Copy i uses slot i % AG_SLOTS: bulk-load peer -> slot (mbarrier), bulk-store
         // slot -> local buffer (bulk group).  Loads run AG_SLOTS - 1 ahead of the stores; a slot is reloaded once the
         // store that read it has finished reading shared memory; a B tile is published to the TMA producers once its
@@ -340,7 +342,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tile_info(i, src, dst, bytes, owner, is_b);
           if (!((seen >> owner) & 1u)) {   // the owner has published this step's chunk?
             const unsigned long long t0 = globaltimer_ns();
-            while (ld_acquire_sys_s32(ag.shard_ready + owner) < ag.epoch) {
+            while (ld_acquire_sys_s32(ag.shard_ready + owner) < want_epoch) {
               __nanosleep(64);
               if (globaltimer_ns() - t0 > 120ull * 1000000000ull) __trap();   // owner never published its shard: fail loudly
             }
@@ -682,7 +684,7 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
     AgParams ag{};
     for (int i = 0; i < 8; ++i) ag.peer[i] = i < a->world ? a->peer[i] : nullptr;
     ag.local = (bf16*)a->local; ag.segs = a->segs; ag.nseg = a->nseg; ag.n_b_segs = a->n_b_segs; ag.total_tiles = a->total_tiles;
-    ag.shard_ready = a->shard_ready; ag.epoch = a->epoch; ag.done = a->done; ag.b_tiles_per_rank = a->b_tiles_per_rank;
+    ag.shard_ready = a->shard_ready; ag.epoch = a->epoch; ag.epoch_ptr = a->epoch_ptr; ag.done = a->done; ag.b_tiles_per_rank = a->b_tiles_per_rank;
     ag.rows_per_rank = a->rows_per_rank; ag.world = a->world; ag.rank = a->rank;
     ZTB_CUDA_CHECK(cudaMemsetAsync(a->done, 0, 8 * sizeof(unsigned), st));
     p.raster_n = 2;

@@ -60,6 +60,7 @@ struct AgParams {
   long long total_tiles;
   const int* shard_ready;       // my flag row: [rank] >= epoch once that rank's chunk is final
   int epoch;
+  const int* epoch_ptr;         // non-null: wait for *epoch_ptr + epoch (device-side step counter, CUDA-graph replays)
   unsigned int* done;           // [8] per-owner count of finished B tiles (zeroed before launch)
   unsigned int b_tiles_per_rank;
   int rows_per_rank;            // B rows owned by each rank
@@ -202,6 +203,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================================================== all-gather warp (NVLink peer pulls)
     if constexpr (AG) {
       unsigned seen = 1u << ag.rank;
+      const int want_epoch = ag.epoch + (ag.epoch_ptr != nullptr ? *ag.epoch_ptr : 0);
       // two gather warps per CTA (warp 6 is free once it has allocated TMEM)
       for (long long t = blockIdx.x * 2 + (warp - 6); t < ag.total_tiles; t += gridDim.x * 2) {
         int lo = 0, hi = ag.nseg - 1;
@@ -215,7 +217,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (lane == 0) {
             unsigned long long t0;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            while (ld_acquire_sys_s32(ag.shard_ready + src) < ag.epoch) {
+            while (ld_acquire_sys_s32(ag.shard_ready + src) < want_epoch) {
               __nanosleep(64);
               unsigned long long t1;
               asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -487,7 +489,7 @@ int ztb_gemm(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
     AgParams ag{};
     for (int i = 0; i < 8; ++i) ag.peer[i] = i < a->world ? a->peer[i] : nullptr;
     ag.local = (bf16*)a->local; ag.segs = a->segs; ag.nseg = a->nseg; ag.n_b_segs = a->n_b_segs; ag.total_tiles = a->total_tiles;
-    ag.shard_ready = a->shard_ready; ag.epoch = a->epoch; ag.done = a->done; ag.b_tiles_per_rank = a->b_tiles_per_rank;
+    ag.shard_ready = a->shard_ready; ag.epoch = a->epoch; ag.epoch_ptr = a->epoch_ptr; ag.done = a->done; ag.b_tiles_per_rank = a->b_tiles_per_rank;
     ag.rows_per_rank = a->rows_per_rank; ag.world = a->world; ag.rank = a->rank;
     ZTB_CUDA_CHECK(cudaMemsetAsync(a->done, 0, 8 * sizeof(unsigned), st));
     p.n_major_raster = 1;

@@ -48,6 +48,7 @@ struct ZtbAdamArgs {
   float inv_bc1, inv_bc2;   // 1 / (1 - beta^step): bias corrections, reciprocal (the kernel multiplies)
   float omb1, omb2;         // 1 - beta1, 1 - beta2
   const float* scale_mul;   // optional device scalar multiplied into grad_scale (global-norm clip coefficient)
+  const float* dyn;         // optional device [lr, inv_bc1, inv_bc2]: overrides the by-value fields (CUDA-graph replays)
 };
 // grads[p] = flat grad buffer of peer p (p = 0 is local); n_peers == 1 -> plain fused AdamW.
 int ztb_adamw_shard(float* master, float* m, float* v, void* flat_param, const void* const* grads, int n_peers,
@@ -60,7 +61,7 @@ enum ZtbEpilogue { ZTB_EPI_NONE = 0, ZTB_EPI_GELU = 1, ZTB_EPI_DROPOUT_ADD = 2, 
 struct ZtbAgArgs {              // all-gather fused into the GEMM (see AgParams in gemm_tcgen05.cu)
   const void* peer[8]; void* local;
   const ZtbSegment* segs; int nseg; int n_b_segs; long long total_tiles;
-  const int* shard_ready; int epoch;
+  const int* shard_ready; int epoch; const int* epoch_ptr;   // epoch_ptr != null: the awaited value is *epoch_ptr + epoch
   unsigned int* done; unsigned int b_tiles_per_rank; int rows_per_rank; int world, rank;
 };
 struct ZtbGemmArgs {
@@ -86,8 +87,8 @@ int ztb_gemm_2cta(const ZtbGemmArgs* args, int sms, cudaStream_t st);
 int ztb_gemm(const ZtbGemmArgs* args, int sms, cudaStream_t st);
 
 // ---- comm.cu (NVLink peer-memory kernels; all pointers are device addresses, peers mapped via symmetric memory)
-int ztb_signal(void* const* pads, int n, int slot, int value, cudaStream_t st);
-int ztb_wait_flags(const int* flags, int n, int value, cudaStream_t st);
+int ztb_signal(void* const* pads, int n, int slot, int value, cudaStream_t st, const int* value_ptr = nullptr);
+int ztb_wait_flags(const int* flags, int n, int value, cudaStream_t st, const int* value_ptr = nullptr);
 int ztb_allgather_pull(void* dst, void* const* srcs, int world, const ZtbSegment* segs, int nseg, long long total_tiles,
                        const int* flags, int wait_value, int sms, cudaStream_t st);
 int ztb_reduce_scatter(void* out, void* const* grads, int n_peers, const ZtbSegment* segs, int nseg, long long total_tiles,

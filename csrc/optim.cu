@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(kAdamThreads, 7) adamw_shard_kernel(float* __r
     __syncthreads();
   }
   const float gscale = a.scale_mul != nullptr ? a.grad_scale * __ldg(a.scale_mul) : a.grad_scale;
+  const float lr = a.dyn != nullptr ? __ldg(a.dyn) : a.lr;
+  const float inv_bc1 = a.dyn != nullptr ? __ldg(a.dyn + 1) : a.inv_bc1, inv_bc2 = a.dyn != nullptr ? __ldg(a.dyn + 2) : a.inv_bc2;
   for (long long t0 = (long long)blockIdx.x * kUnroll; t0 < total_tiles; t0 += (long long)gridDim.x * kUnroll) {
     int sgi[kUnroll];          // segment of tile t0 + k, or -1: nothing to do for this slot
     int e0[kUnroll];           // this thread's first element inside that segment's chunk (chunks are < 2^31 elements)
@@ -162,8 +164,8 @@ __global__ void __launch_bounds__(kAdamThreads, 7) adamw_shard_kernel(float* __r
         if (a.clip > 0.f) gg = fminf(fmaxf(gg, -a.clip), a.clip);
         float mk = a.beta1 * mf[j] + a.omb1 * gg;
         float vk = a.beta2 * vf[j] + a.omb2 * gg * gg;
-        float upd = (mk * a.inv_bc1) / (sqrtf(vk * a.inv_bc2) + a.eps) + wd * pf[j];
-        pf[j] -= a.lr * upd;
+        float upd = (mk * inv_bc1) / (sqrtf(vk * inv_bc2) + a.eps) + wd * pf[j];
+        pf[j] -= lr * upd;
         mf[j] = mk;
         vf[j] = vk;
       }

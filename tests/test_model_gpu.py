@@ -261,3 +261,36 @@ def _resume_body(tmp_path, train, json):
     for n in pa["params"]:
         assert torch.equal(pa["params"][n], pb["params"][n]), n
     assert pa["rng"] == pb["rng"]
+
+
+def test_cuda_graph_step_matches_eager_steps(tmp_path):
+    """training.cuda_graph: the replayed graph must produce the same parameters as eager steps (same batches, dropout on:
+    the Philox offset advances inside the graph; lr / bias corrections come from device memory)."""
+    from zero_transformer_b200.config import DEFAULT_MODEL_CFG, load_config
+    from zero_transformer_b200.parallel import dist as pdist
+    from zero_transformer_b200.train import Trainer
+
+    import zero_transformer_b200.ops.cuda as C
+
+    C.CONFIG.deterministic = True
+    try:
+        outs = []
+        for graph in (False, True):
+            over = ["model.size=125m", "training.batch_size=8", "training.train_context=256", "data.max_context=256",
+                    "training.gradient_accumulation_steps=2", "training.evaluation_frequency=0", "training.warmup_steps=2",
+                    "training.total_steps=10", f"data.bucket_path={tmp_path}", f"training.cuda_graph={'true' if graph else 'false'}",
+                    "training.cuda_graph_warmup=2"]
+            tr = Trainer(load_config(None, over), DEFAULT_MODEL_CFG, pdist.setup_dp(), log_metrics=False, synthetic=True)
+            g = torch.Generator().manual_seed(11)
+            losses = []
+            for _ in range(6):
+                x = torch.randint(0, 50304, (8, 256), generator=g, dtype=torch.int32).cuda()
+                losses.append(float(tr.train_step(x)["train/loss"]))
+            tr.engine.synchronize()
+            assert (tr._graph is not None) == graph
+            outs.append((tr.engine.master.clone(), losses, tr.engine.step_count))
+        assert outs[0][2] == outs[1][2] == 6
+        assert outs[0][1] == outs[1][1], (outs[0][1], outs[1][1])
+        assert torch.equal(outs[0][0], outs[1][0])
+    finally:
+        C.CONFIG.deterministic = False

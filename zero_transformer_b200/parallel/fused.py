@@ -129,6 +129,11 @@ class FusedComm:
         self.ag_two_cta = os.environ.get("ZTB_AG_2CTA", "1") == "1"
         self._ag_pending = [False] * self.nb
         self.epoch = 0
+        # CUDA-graph mode: a replayed launch cannot carry a new step number, so the counter also lives on the device and
+        # the flag kernels are passed (offset 0, pointer) instead of the value.  ``begin_step`` bumps both copies; the
+        # graph replays the device-side bump, the replay wrapper (Zero1Engine.after_graph_replay) the host-side one.
+        self.graph_mode = False
+        self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=device)
         self.stream = torch.cuda.Stream(device)
         self.sm_count = torch.cuda.get_device_properties(device).multi_processor_count
         self.ready = [torch.cuda.Event() for _ in range(self.nb)]       # bucket b usable by compute
@@ -155,16 +160,34 @@ class FusedComm:
     def _my_row(self, kind: int, bucket: int) -> int:
         return self._flags.ptrs[self.rank] + 4 * self._slot(kind, bucket, 0)
 
+    def _ev(self, value: int):
+        """(value, value_ptr) for the flag kernels: the literal step number, or (0, &epoch_dev) in CUDA-graph mode."""
+        return (0, self.epoch_dev.data_ptr()) if self.graph_mode else (int(value), 0)
+
     def _signal(self, kind: int, bucket: int, value: int) -> None:
-        self._C.signal(self._flags.ptrs, self._slot(kind, bucket, self.rank), value)
+        v, ptr = self._ev(value)
+        self._C.signal(self._flags.ptrs, self._slot(kind, bucket, self.rank), v, ptr)
+
+    def _wait(self, kind: int, bucket: int, value: int) -> None:
+        v, ptr = self._ev(value)
+        self._C.wait_flags(self._my_row(kind, bucket), self.world, v, ptr)
+
+    def set_graph_mode(self, on: bool) -> None:
+        if on and not self.graph_mode:
+            self.epoch_dev.fill_(self.epoch)
+        self.graph_mode = bool(on)
 
     # per-step protocol --------------------------------------------------
     def begin_step(self) -> None:
         self.epoch += 1
+        if self.graph_mode:
+            # on the compute stream: after this step's forward (whose waits still mean the previous step) and before every
+            # flag kernel of this step (bucket_update makes the communication stream wait on the compute stream first)
+            self.epoch_dev.add_(1)
         self._pushed = [False] * self.nb
 
     def bucket_update(self, b: int, *, master, m, v, lr, beta1, beta2, eps, wd, step, clip, grad_scale, background: bool = False,
-                      reduced: bool = False, scale_mul: Optional[torch.Tensor] = None) -> None:
+                      reduced: bool = False, scale_mul: Optional[torch.Tensor] = None, dyn: Optional[torch.Tensor] = None) -> None:
         """Bucket ``b``'s gradients are final on the current (compute) stream: reduce-scatter them
         from every peer, apply AdamW to the owned shard and publish the new bf16 chunk.
 
@@ -178,14 +201,15 @@ class FusedComm:
             self.stream.wait_event(self._ev)
             if self.world > 1 and not reduced:
                 self._signal(FLAG_GRAD_READY, b, e)
-                self._C.wait_flags(self._my_row(FLAG_GRAD_READY, b), self.world, e)
+                self._wait(FLAG_GRAD_READY, b, e)
             segs, n, tiles = self.adam[b]
             # reduced=True: bucket_reduce() already left the cross-rank sum in the local buffer
             ptrs = self._grad.ptrs[self.rank:self.rank + 1] if (reduced or self.world == 1) else self.grad_ptrs
             mc_grad = self._grad.multicast_ptr if (self.nvls and not reduced) else 0
             mc_param = self._param.multicast_ptr if self.nvls else 0
             self._C.adamw_shard(master, m, v, self.flat_param, ptrs, self.grad_fp32, segs, n, tiles, lr, beta1, beta2, eps, wd, clip,
-                                grad_scale, step, 0, 0, self.sm_count if background else 0, scale_mul.data_ptr() if scale_mul is not None else 0, mc_grad, mc_param)
+                                grad_scale, step, 0, 0, self.sm_count if background else 0, scale_mul.data_ptr() if scale_mul is not None else 0, mc_grad, mc_param,
+                                dyn.data_ptr() if dyn is not None else 0)
             self._pushed[b] = bool(mc_param)
             if self.world > 1:
                 self._signal(FLAG_SHARD_READY, b, e)
@@ -204,7 +228,7 @@ class FusedComm:
             self.stream.wait_event(self._ev)
             if self.world > 1:
                 self._signal(FLAG_GRAD_READY, b, e)
-                self._C.wait_flags(self._my_row(FLAG_GRAD_READY, b), self.world, e)
+                self._wait(FLAG_GRAD_READY, b, e)
                 segs, n, tiles = self.rs_inplace[b]
                 self._C.reduce_scatter(self.flat_grad, self.grad_ptrs, segs, n, tiles, 0, 0)
 
@@ -223,7 +247,7 @@ class FusedComm:
             for b in range(self.nb):
                 if b in fused_buckets or self._pushed[b]:
                     continue
-                self._C.wait_flags(self._my_row(FLAG_SHARD_READY, b), self.world, e)
+                self._wait(FLAG_SHARD_READY, b, e)
                 segs, n, tiles = self.pull[b]
                 self._C.allgather_pull(self.flat_param, self._param.ptrs, segs, n, tiles, 0, 0)
                 self.ready[b].record(self.stream)
@@ -254,8 +278,8 @@ class FusedComm:
         two_cta = self.ag_two_cta and (plan0 := self.ag_plan(b, first_region, AG2_TILE))["rows_per_rank"] % 128 == 0
         plan = plan0 if two_cta else self.ag_plan(b, first_region)
         out = self._C.gemm_ag(x2, w, self._param.ptrs, self.flat_param, plan["segs"], plan["nseg"], plan["n_b"], plan["tiles"],
-                              self._my_row(FLAG_SHARD_READY, b), self.epoch, self.ag_done, plan["b_tiles"], plan["rows_per_rank"],
-                              self.world, self.rank, two_cta)
+                              self._my_row(FLAG_SHARD_READY, b), self._ev(self.epoch)[0], self.ag_done, plan["b_tiles"], plan["rows_per_rank"],
+                              self.world, self.rank, two_cta, self._ev(self.epoch)[1])
         self._ag_pending[b] = False
         self._pending[b] = False
         return out
@@ -266,14 +290,14 @@ class FusedComm:
             # nobody ran the fused GEMM for this bucket (e.g. state access before the next forward):
             # fall back to the standalone pull on the compute stream
             self._ag_pending[b] = False
-            self._C.wait_flags(self._my_row(FLAG_SHARD_READY, b), self.world, self.epoch)
+            self._wait(FLAG_SHARD_READY, b, self.epoch)
             segs, n, tiles = self.pull[b]
             self._C.allgather_pull(self.flat_param, self._param.ptrs, segs, n, tiles, 0, 0)
             self._pending[b] = False
             return
         if self._flagwait[b]:
             self._flagwait[b] = False
-            self._C.wait_flags(self._my_row(FLAG_SHARD_READY, b), self.world, self.epoch)   # one warp, compute stream
+            self._wait(FLAG_SHARD_READY, b, self.epoch)   # one warp, compute stream
             self._pending[b] = False
             return
         if self._pending[b]:

@@ -149,6 +149,7 @@ class Zero1Engine:
                 else:
                     p.grad = L.view(self.flat_grad, n)
         self._named = named
+        self._dyn = None
         # Lazy zero_grad (first micro-batch overwrites instead of accumulating) is only sound when every parameter's
         # gradient is produced by a fused writer that honours the overwrite mode.  The op layer falls back to plain
         # autograd accumulation for shapes its kernels do not take (last dim or vocabulary not a multiple of 8); with such
@@ -179,9 +180,53 @@ class Zero1Engine:
 
     # -- fused-backend hooks ---------------------------------------------
     def _adam_kwargs(self):
-        return dict(master=self.master, m=self.exp_avg, v=self.exp_avg_sq, lr=self.lr, beta1=self.beta1, beta2=self.beta2,
-                    eps=self.eps, wd=self.weight_decay, step=self.step_count + 1, clip=self.clip or 0.0,
-                    grad_scale=1.0 / (self.world * self.grad_accum_steps))
+        kw = dict(master=self.master, m=self.exp_avg, v=self.exp_avg_sq, lr=self.lr, beta1=self.beta1, beta2=self.beta2,
+                  eps=self.eps, wd=self.weight_decay, step=self.step_count + 1, clip=self.clip or 0.0,
+                  grad_scale=1.0 / (self.world * self.grad_accum_steps))
+        if self._dyn is not None:
+            kw["dyn"] = self._dyn     # CUDA-graph mode: lr and the bias corrections are read from the device
+        return kw
+
+    # -- CUDA-graph support ------------------------------------------------
+    def enable_graph_mode(self) -> None:
+        """Make one optimizer step replayable as a CUDA graph: everything that changes from step to step and used to be
+        a launch argument (learning rate, Adam bias corrections, the flag protocol's step number) is read from device
+        memory instead.  Call ``stage_step_scalars()`` before each replay and ``after_graph_replay()`` after it."""
+        if self._fused is None:
+            raise RuntimeError("graph mode needs the fused backend")
+        if self._two_phase:
+            raise RuntimeError("graph mode does not support clip_mode=global_norm (host-visible all-reduce inside the step)")
+        self._dyn = torch.zeros(3, dtype=torch.float32, device=self.device)
+        # ring of pinned staging slots: the host may run several replays ahead of the device, and an async copy reads its
+        # pinned source when it EXECUTES -- a slot is rewritten only after the copy that last used it has run
+        self._dyn_host = [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in range(8)]
+        self._dyn_ev = [None] * 8
+        self._dyn_i = 0
+        self._fused.set_graph_mode(True)
+        self.stage_step_scalars()
+
+    def stage_step_scalars(self) -> float:
+        """Upload (lr, 1/(1-b1^t), 1/(1-b2^t)) of the update about to run; stream-ordered, no host sync."""
+        t = self.step_count + 1
+        lr = self.lr
+        i = self._dyn_i
+        self._dyn_i = (i + 1) % len(self._dyn_host)
+        if self._dyn_ev[i] is not None:
+            self._dyn_ev[i].synchronize()
+        h = self._dyn_host[i]
+        h[0] = lr
+        h[1] = 1.0 / (1.0 - self.beta1 ** t)
+        h[2] = 1.0 / (1.0 - self.beta2 ** t)
+        self._dyn.copy_(h, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._dyn_ev[i] = ev
+        return lr
+
+    def after_graph_replay(self) -> None:
+        """Host-side bookkeeping that the captured ``step()`` did once at capture time."""
+        self.step_count += 1
+        self._fused.epoch += 1
 
     def _on_block_backward_done(self, i: int) -> None:
         """Block ``i``'s backward just finished on the last micro-batch: its bucket's gradients are

@@ -110,7 +110,14 @@ class Trainer:
                                     run_id=ckpt.stable_run_id(self.workdir) if env.is_main else None)
         self._timer = StepTimer(env.device)
         self._nvtx = on_gpu and os.environ.get("ZTB_NVTX", "0") == "1"   # NVTX ranges for nsys/ncu timelines
+        # training.cuda_graph (or ZTB_CUDA_GRAPH=1): capture one whole optimizer step (all micro-batches, the per-bucket
+        # updates on the communication stream, the all-gather waits) into a CUDA graph after `graph_warmup` eager steps
+        # and replay it from then on -- one launch per step instead of ~1100, no inter-kernel launch gaps.
+        env_graph = os.environ.get("ZTB_CUDA_GRAPH")
+        self.use_graph = on_gpu and (bool(t.get("cuda_graph", False)) if env_graph is None else env_graph == "1")
+        self.graph_warmup = int(t.get("cuda_graph_warmup", 3))
         self._graph = None
+        self._eager_steps = 0
 
     # ------------------------------------------------------------------ data
     def _samples(self, split: str) -> Iterable[np.ndarray]:
@@ -155,6 +162,48 @@ class Trainer:
     def train_step(self, batch: torch.Tensor) -> Dict[str, torch.Tensor]:
         """One optimizer update from a ``(rows_per_rank, max_context)`` token
         batch already on the device.  Returns device tensors (no host sync)."""
+        if self.use_graph:
+            if self._graph is not None:
+                return self._replay(batch)
+            if self._eager_steps >= self.graph_warmup:
+                self._capture(batch)
+                return self._replay(batch)
+            self._eager_steps += 1
+        return self._train_step_eager(batch)
+
+    # -- CUDA graph --------------------------------------------------------
+    def _capture(self, batch: torch.Tensor) -> None:
+        from .ops import cuda as K
+
+        eng = self.engine
+        eng.synchronize()                      # no pending cross-step waits may leak into the capture
+        eng.enable_graph_mode()
+        self._g_in = batch.clone()
+        torch.cuda.synchronize(self.env.device)
+        before = K.LAUNCHES.count
+        snap = (eng.step_count, eng._fused.epoch)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            out = self._train_step_eager(self._g_in, in_capture=True)
+        self._g_loss = out["train/loss"]
+        self._g_launches = K.LAUNCHES.count - before
+        K.LAUNCHES.count = before              # the capture pass launched nothing
+        # the captured body ran the host-side bookkeeping once without executing anything: rewind it
+        eng.step_count, eng._fused.epoch = snap
+        self.log.debug("captured one optimizer step as a CUDA graph (%d kernel launches)", self._g_launches)
+
+    def _replay(self, batch: torch.Tensor) -> Dict[str, torch.Tensor]:
+        from .ops import cuda as K
+
+        eng = self.engine
+        self._g_in.copy_(batch, non_blocking=True)
+        lr = eng.stage_step_scalars()
+        self._graph.replay()
+        eng.after_graph_replay()
+        K.LAUNCHES.count += self._g_launches
+        return {"train/loss": self._g_loss, "lr": lr}
+
+    def _train_step_eager(self, batch: torch.Tensor, in_capture: bool = False) -> Dict[str, torch.Tensor]:
         self.model.train()
         nvtx = self._nvtx
         if nvtx:
@@ -169,6 +218,11 @@ class Trainer:
         if nvtx:
             torch.cuda.nvtx.range_push("optimizer_step")
         lr = self.engine.step()
+        if in_capture:
+            # self-contained graph: join the communication stream and consume every bucket's "ready" signal here instead
+            # of in the next step's forward hooks (costs the overlap of the last buckets' update with the next forward)
+            self.engine._fused.wait_all()
+            torch.cuda.current_stream(self.env.device).wait_stream(self.engine._fused.stream)
         if nvtx:
             torch.cuda.nvtx.range_pop()
             torch.cuda.nvtx.range_pop()
