@@ -15,6 +15,10 @@ cat gpurun_out/r2_bench_dq16.json
 ZTB_PDL=1 timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_model_gpu.py -x -q -m gpu -k "not resume and not train_cli" > gpurun_out/r2_tests_pdl.log 2>&1; echo "pdl tests rc=$?" >> gpurun_out/r2_tests_pdl.log; tail -n 3 gpurun_out/r2_tests_pdl.log
 ZTB_PDL=1 timeout 600 python bench.py --steps 6 --warmup 3 2>gpurun_out/r2_bench_pdl.err | tail -1 > gpurun_out/r2_bench_pdl.json
 cat gpurun_out/r2_bench_pdl.json
+ZTB_LMHEAD_2CTA=1 timeout 600 python bench.py --steps 6 --warmup 3 2>gpurun_out/r2_bench_lm2.err | tail -1 > gpurun_out/r2_bench_lm2.json
+cat gpurun_out/r2_bench_lm2.json
+ZTB_GEMM_DIRECT=1 timeout 600 python bench.py --steps 6 --warmup 3 2>gpurun_out/r2_bench_direct1.err | tail -1 > gpurun_out/r2_bench_direct1.json
+cat gpurun_out/r2_bench_direct1.json
 ZTB_CUDA_GRAPH=1 timeout 600 python bench.py --steps 6 --warmup 3 2>gpurun_out/r2_bench_graph.err | tail -1 > gpurun_out/r2_bench_graph.json
 cat gpurun_out/r2_bench_graph.json; tail -n 3 gpurun_out/r2_bench_graph.err
 timeout 600 python bench/gap_analysis.py > gpurun_out/r2_gap.txt 2>&1

@@ -51,10 +51,11 @@ class _Counting:
             def wrapped(*a, **k):
                 LAUNCHES.count += 1
                 if "two_cta" not in k and CONFIG.gemm_2cta:
-                    # measured on B200: the CTA-pair kernel wins everywhere except the vocabulary-sized
-                    # GEMMs (N or K = 50304), where the 1-CTA raster keeps more of wte in L2
+                    # round 1 measured the CTA-pair kernel ahead everywhere except the vocabulary-sized GEMMs
+                    # (N or K = 50304) with its row-block-group raster; `lmhead_2cta` sends those to the CTA-pair kernel
+                    # too (column-block-group raster for the forward GEMM, see ztb_gemm_2cta)
                     big = max(a[0].shape[0], a[0].shape[1], a[1].shape[0], a[1].shape[1]) > 20000
-                    k["two_cta"] = not big
+                    k["two_cta"] = (not big) or CONFIG.lmhead_2cta
                 return fn(*a, **k)
         else:
             def wrapped(*a, **k):
@@ -76,6 +77,7 @@ class _Config:
     tc_gemm_bwd = os.environ.get("ZTB_TC_GEMM_BWD", "1") == "1"  # MN-major dgrad/wgrad on tcgen05
     fuse_wgrad = os.environ.get("ZTB_FUSE_WGRAD", "1") == "1"    # accumulate dW into param.grad in the epilogue
     gemm_2cta = os.environ.get("ZTB_GEMM_2CTA", "1") == "1"      # cta_group::2 256x256 kernel for the big GEMMs
+    lmhead_2cta = os.environ.get("ZTB_LMHEAD_2CTA", "0") == "1"   # vocabulary-sized GEMMs on the CTA-pair kernel as well
     attn_impl = os.environ.get("ZTB_ATTN", "auto")                # auto | tc (own kernel) | flash (flash_attn library) | ref
     # head_dim 128: accumulate dQ over key blocks directly in the bf16 dqkv buffer (no fp32 scratch, zero-fill, convert pass)
     attn_dq_bf16 = os.environ.get("ZTB_ATTN_DQ_BF16", "0") == "1"
