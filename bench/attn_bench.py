@@ -39,11 +39,15 @@ from zero_transformer_b200.ops.attention_cuda import alibi_attention
 
 qg = qkv.clone().requires_grad_(True)
 dout = torch.randn(B, T, H * hd, device="cuda").bfloat16()
-for p in (0.0, 0.1):
-    K.begin_forward("cuda")
-    o = alibi_attention(qg, slopes, H, hd ** -0.5, p)
-    t = timeit(lambda: o.backward(dout, retain_graph=True))
-    print(json.dumps({"kernel": "ztb_attn_bwd(+delta+convert)", "dropout": p, "ms": round(t, 4), "tflops_causal": round(2.5 * fl / t / 1e9, 1)}))
+for dq16 in (False, True):
+    K.CONFIG.attn_dq_bf16 = dq16
+    for p in (0.0, 0.1):
+        K.begin_forward("cuda")
+        o = alibi_attention(qg, slopes, H, hd ** -0.5, p)
+        t = timeit(lambda: o.backward(dout, retain_graph=True))
+        print(json.dumps({"kernel": "ztb_attn_bwd(+delta" + ("+bf16 dQ reduce" if dq16 else "+fp32 dQ scratch+convert") + ")", "dropout": p,
+                          "ms": round(t, 4), "tflops_causal": round(2.5 * fl / t / 1e9, 1)}))
+K.CONFIG.attn_dq_bf16 = False
 of = flash_attn_qkvpacked_func(qg.view(B, T, 3, H, hd), 0.0, hd ** -0.5, True, alibi_slopes=slopes)
 t = timeit(lambda: of.backward(dout.view(B, T, H, hd), retain_graph=True))
 print(json.dumps({"kernel": "flash_attn2_bwd", "ms": round(t, 4), "tflops_causal": round(2.5 * fl / t / 1e9, 1)}))
