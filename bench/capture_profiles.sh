@@ -3,7 +3,7 @@
 set -x
 mkdir -p gpurun_out
 NCU="ncu --set full --clock-control none --import-source on"
-$NCU -k regex:gemm2?_tcgen05 -s 15 -c 5 -f -o gpurun_out/prof_gemm python bench/prof_kernels.py gemm > gpurun_out/prof_gemm.log 2>&1
+$NCU -k regex:gemm2?_tcgen05 -s 10 -c 5 -f -o gpurun_out/prof_gemm python bench/prof_kernels.py gemm > gpurun_out/prof_gemm.log 2>&1
 $NCU -k regex:attn_ -s 8 -c 4 -f -o gpurun_out/prof_attn python bench/prof_kernels.py attn > gpurun_out/prof_attn.log 2>&1
 $NCU -k regex:"adamw|layernorm|ce_" -s 5 -c 5 -f -o gpurun_out/prof_misc python bench/prof_kernels.py misc > gpurun_out/prof_misc.log 2>&1
 python bench/profile_step.py > gpurun_out/step_profile.txt 2>&1
