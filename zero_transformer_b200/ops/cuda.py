@@ -77,6 +77,7 @@ class _Config:
     tc_gemm_bwd = os.environ.get("ZTB_TC_GEMM_BWD", "1") == "1"  # MN-major dgrad/wgrad on tcgen05
     fuse_wgrad = os.environ.get("ZTB_FUSE_WGRAD", "1") == "1"    # accumulate dW into param.grad in the epilogue
     gemm_2cta = os.environ.get("ZTB_GEMM_2CTA", "1") == "1"      # cta_group::2 256x256 kernel for the big GEMMs
+    ce_chunk_rows = int(os.environ.get("ZTB_CE_CHUNK_ROWS", "0"))   # > 0: chunked LM head + CE (logits of one chunk at a time)
     lmhead_2cta = os.environ.get("ZTB_LMHEAD_2CTA", "0") == "1"   # vocabulary-sized GEMMs on the CTA-pair kernel as well
     attn_impl = os.environ.get("ZTB_ATTN", "auto")                # auto | tc (own kernel) | flash (flash_attn library) | ref
     # head_dim 128: accumulate dQ over key blocks directly in the bf16 dqkv buffer (no fp32 scratch, zero-fill, convert pass)
@@ -94,7 +95,7 @@ CONFIG = _Config()
 # buffer): accumulate (beta = 1) or overwrite (beta = 0).  The engine switches to overwrite for the
 # first micro-batch of a step, which removes the gradient memset and the read half of the first
 # accumulation.
-GRAD_MODE = {"accumulate": True}
+GRAD_MODE = {"accumulate": True, "lazy_zero": False}   # lazy_zero: the engine skipped the memset; the next writer of each buffer overwrites
 
 # ---------------------------------------------------------------------------
 # Dropout RNG: one device-resident (seed, offset) pair per device so the whole
@@ -538,9 +539,74 @@ class _LMHeadLoss(torch.autograd.Function):
         return dh, dw, None
 
 
+class _LMHeadLossChunked(torch.autograd.Function):
+    """Chunked LM head + cross entropy (``training.ce_chunk_rows`` / ``ZTB_CE_CHUNK_ROWS``): the token
+    rows are processed ``chunk`` at a time -- logits GEMM, single-pass CE forward, dlogits in place, dgrad GEMM into the
+    rows' slice of dh, wgrad accumulated into the tied embedding's gradient buffer -- so only ``chunk x V`` logits ever
+    exist (1.65 GB -> 0.1-0.2 GB at 16k tokens per micro-batch) and nothing is recomputed in backward.
+
+    Trade: the gradients are produced during *forward* under the assumption that the loss is differentiated with a unit
+    upstream gradient (what ``Zero1Engine.backward`` / ``loss.backward()`` do); backward only scales the stored dh by the
+    actual upstream gradient, so a caller that backpropagates ``k * loss`` gets dh right but the embedding's head gradient
+    unscaled -- use the unchunked path for that.  The per-chunk wgrad (K = chunk rows) re-reads and re-writes the whole
+    (V, D) gradient each time, which is why this is an option for memory-bound shapes and not the default on a 180 GB part."""
+
+    @staticmethod
+    def forward(ctx, h, wte, tokens, chunk):
+        B, T, D = h.shape
+        M = B * T
+        h2 = h.reshape(M, D)
+        labels = torch.full((B, T), -1, dtype=torch.int32, device=h.device)
+        labels[:, :-1] = tokens[:, 1:].to(torch.int32)
+        labels = labels.view(-1)
+        count = B * (T - 1)
+        need_grad = torch.is_grad_enabled() and (h.requires_grad or wte.requires_grad)
+        dh = torch.empty_like(h2) if need_grad else None
+        one = torch.ones(1, dtype=torch.float32, device=h.device)
+        total = torch.zeros((), dtype=torch.float32, device=h.device)
+        tgt = _grad_target(wte) if need_grad else None
+        dw = None
+        first_acc = GRAD_MODE["accumulate"] and not GRAD_MODE.get("lazy_zero", False)
+        for i, s0 in enumerate(range(0, M, chunk)):
+            e0 = min(s0 + chunk, M)
+            logits = _mm_fwd(h2[s0:e0], wte)
+            lse, nll = _C.ce_fwd(logits, labels[s0:e0])
+            total = total + nll.sum()
+            if not need_grad:
+                continue
+            _C.ce_bwd_(logits, labels[s0:e0], lse, one, 1.0 / count)
+            if CONFIG.tc_gemm_bwd and _tc_ok(e0 - s0, D, wte.shape[0]) and (e0 - s0) % 8 == 0:
+                _C.gemm(logits, wte, C=dh[s0:e0], b_mn=True)      # dgrad straight into the rows' slice of dh
+            else:
+                dh[s0:e0].copy_(logits @ wte)
+            if tgt is not None:
+                acc = first_acc or i > 0
+                if CONFIG.tc_gemm_bwd and _tc_ok(wte.shape[0], D, e0 - s0):
+                    _C.gemm(logits, h2[s0:e0], C=tgt, accumulate=acc, a_mn=True, b_mn=True)
+                elif acc:
+                    tgt.add_((logits.t() @ h2[s0:e0]).to(tgt.dtype))
+                else:
+                    tgt.copy_(logits.t() @ h2[s0:e0])
+            else:
+                part = logits.t() @ h2[s0:e0]
+                dw = part if dw is None else dw + part
+        ctx.save_for_backward(dh if dh is not None else h2.new_empty(0), dw if dw is not None else h2.new_empty(0))
+        ctx.meta = (h.shape, dw is not None)
+        return total / count
+
+    @staticmethod
+    def backward(ctx, gout):
+        dh, dw = ctx.saved_tensors
+        hshape, has_dw = ctx.meta
+        g = gout.reshape(1).to(dh.dtype)
+        return (dh * g).view(hshape), ((dw * g).to(dw.dtype) if has_dw else None), None, None
+
+
 def lm_head_loss(h, wte, tokens):
     if wte.shape[0] % 8 or h.dtype != torch.bfloat16:
         return reference.lm_head_loss(h, wte, tokens)
+    if CONFIG.ce_chunk_rows > 0 and h.shape[0] * h.shape[1] > CONFIG.ce_chunk_rows:
+        return _LMHeadLossChunked.apply(h, wte, tokens, int(CONFIG.ce_chunk_rows))
     return _LMHeadLoss.apply(h, wte, tokens)
 
 

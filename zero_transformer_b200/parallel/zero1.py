@@ -286,6 +286,7 @@ class Zero1Engine:
             loss.backward()
         finally:
             K.GRAD_MODE["accumulate"] = True
+            K.GRAD_MODE["lazy_zero"] = False
             self._in_engine_backward = False
         self._overwrite_next = False
         self._fold_stray_grads()
@@ -305,6 +306,9 @@ class Zero1Engine:
         memset, the next backward overwrites instead of accumulating."""
         if lazy and self._fused is not None and self._lazy_ok:
             self._overwrite_next = True
+            from ..ops import cuda as K
+
+            K.GRAD_MODE["lazy_zero"] = True    # seen by gradient writers that run before engine.backward (chunked LM head)
             return
         self.flat_grad.zero_()
         if self.main_grads:

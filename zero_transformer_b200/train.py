@@ -108,6 +108,10 @@ class Trainer:
                             "Total Devices": env.world})
             self.sink = MetricsSink(self.workdir, run_cfg, project=str(d.get("wandb_project", "") or ""), enabled=env.is_main,
                                     run_id=ckpt.stable_run_id(self.workdir) if env.is_main else None)
+        if on_gpu and int(t.get("ce_chunk_rows", 0) or 0) > 0:
+            from .ops import cuda as K
+
+            K.CONFIG.ce_chunk_rows = int(t.ce_chunk_rows)
         self._timer = StepTimer(env.device)
         self._nvtx = on_gpu and os.environ.get("ZTB_NVTX", "0") == "1"   # NVTX ranges for nsys/ncu timelines
         # training.cuda_graph (or ZTB_CUDA_GRAPH=1): capture one whole optimizer step (all micro-batches, the per-bucket
