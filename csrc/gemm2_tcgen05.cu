@@ -665,11 +665,12 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
   p.p = g->p; p.inv_keep = g->p < 1.f ? 1.f / (1.f - g->p) : 0.f;
   p.rng = g->rng; p.op_id = g->op_id;
   p.tiles_m = (g->M + TILE_M - 1) / TILE_M; p.tiles_n = (g->N + BN - 1) / BN; p.num_tiles = p.tiles_m * p.tiles_n;
-  // Raster: groups of GROUP_M row blocks sweep all column blocks (B panel streams, A group stays hot) -- unless N is
-  // vocabulary-sized: then groups of column blocks sweep all row blocks, so the 10^2 MB activation panel is re-read
-  // from L2 and the weight streams through once.
+  // Raster: groups of GROUP_M row blocks sweep all column blocks (the B operand streams once per group, the A group stays
+  // hot) -- unless B is the larger operand (more column blocks than row blocks: the LM head, 197 vs 64): then groups of
+  // column blocks sweep all row blocks, so the activation panel (67 MB, L2-resident) is what gets re-read and the
+  // 206 MB embedding streams through exactly once.
   static const int raster_env = env_int("ZTB_GEMM_RASTER_N", -1);
-  p.raster_n = g->raster_n >= 0 ? g->raster_n : (raster_env >= 0 ? raster_env : (p.tiles_n > 4 * p.tiles_m ? 1 : 0));
+  p.raster_n = g->raster_n >= 0 ? g->raster_n : (raster_env >= 0 ? raster_env : (p.tiles_n > p.tiles_m ? 1 : 0));
   int pairs = sms / 2;
   // Wave quantisation: num_tiles is rarely a multiple of the 74 CTA pairs (weight gradients: 64 / 192 / 256
   // tiles).  Cut each tile of the last, partial wave into `split` K-ranges so that it costs
