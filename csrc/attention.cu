@@ -1178,13 +1178,13 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const CUten
 // head_dim 128: dQ is then accumulated directly in dqkv in bf16 (see AttnBwdParams::dq_bf16); delta: [B,H,T] fp32 scratch.
 int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dq_acc, float* delta,
                  const float* slopes, int B, int T, int H, int hd, float scale, float dropout_p, const uint64_t* rng,
-                 uint32_t op_id, int sms, cudaStream_t st, unsigned long long* dbg) {
+                 uint32_t op_id, int sms, cudaStream_t st, unsigned long long* dbg, int delta_ready) {
   if (T % 128 != 0 || (hd != 64 && hd != 96 && hd != 128)) {
     ztb_set_error("ztb_attn_bwd", "needs T % 128 == 0 and head_dim in {64, 96, 128}", __FILE__, __LINE__);
     return -1;
   }
   const long long D = (long long)H * hd, rows = (long long)B * T;
-  {
+  if (!delta_ready) {
     const long long nr = rows * H;
     const int rpw = 32 / (hd / 8);
     const unsigned blocks = (unsigned)((nr + 8 * rpw - 1) / (8 * rpw));

@@ -165,7 +165,7 @@ void ce_bwd_(at::Tensor& logits, const at::Tensor& labels, const at::Tensor& lse
 at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tensor> C_, int64_t epilogue,
                 const c10::optional<at::Tensor>& aux_in, c10::optional<at::Tensor> aux_out, double p,
                 const c10::optional<at::Tensor>& rng, int64_t op_id, bool accumulate, bool a_mn, bool b_mn, bool two_cta, bool no_split,
-                int64_t direct_store, int64_t raster_n) {
+                int64_t direct_store, int64_t raster_n, c10::optional<at::Tensor> rowdot_out, int64_t rowdot_T, int64_t rowdot_hd) {
   need(is_bf16_cuda(A) && is_bf16_cuda(B) && A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "gemm: A, B must be 2-D bf16 CUDA with unit inner stride");
   c10::cuda::CUDAGuard g(A.device());
   ZtbGemmArgs a{};
@@ -202,6 +202,12 @@ at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tens
     a.rng = (const uint64_t*)rng->data_ptr<int64_t>();
   }
   need(epilogue != ZTB_EPI_DROPOUT_ADD || a.rng != nullptr, "gemm: dropout epilogue needs rng");
+  if (rowdot_out.has_value()) {
+    need(rowdot_out->is_cuda() && rowdot_out->scalar_type() == at::kFloat && rowdot_out->is_contiguous() && rowdot_hd > 0 &&
+         rowdot_out->numel() == (int64_t)a.M * (a.N / rowdot_hd), "gemm: rowdot_out must be fp32 contiguous with M * N / head_dim elements");
+    a.rowdot_out = rowdot_out->data_ptr<float>(); a.rowdot_T = (int)rowdot_T; a.rowdot_hd = (int)rowdot_hd;
+  }
+  need(epilogue != ZTB_EPI_ROWDOT || (a.rowdot_out != nullptr && two_cta), "gemm: ROWDOT epilogue needs rowdot_out and two_cta");
   check(ztb_gemm(&a, num_sms(), stream()), "gemm");
   return C;
 }
@@ -278,7 +284,8 @@ std::vector<at::Tensor> attention_fwd(const at::Tensor& qkv, const c10::optional
 
 at::Tensor attention_bwd(const at::Tensor& qkv, const at::Tensor& out, const at::Tensor& dout, const at::Tensor& lse,
                          const c10::optional<at::Tensor>& slopes, int64_t H, double scale, double p,
-                         const c10::optional<at::Tensor>& rng, int64_t op_id, const c10::optional<at::Tensor>& dbg, bool dq_bf16) {
+                         const c10::optional<at::Tensor>& rng, int64_t op_id, const c10::optional<at::Tensor>& dbg, bool dq_bf16,
+                         const c10::optional<at::Tensor>& delta_in) {
   need(is_bf16_cuda(qkv) && qkv.dim() == 3 && qkv.is_contiguous() && is_bf16_cuda(out) && out.is_contiguous() && is_bf16_cuda(dout) && dout.is_contiguous(),
        "attention_bwd: bf16 contiguous tensors");
   c10::cuda::CUDAGuard g(qkv.device());
@@ -287,12 +294,19 @@ at::Tensor attention_bwd(const at::Tensor& qkv, const at::Tensor& out, const at:
   const bool dq16 = dq_bf16 && hd == 128;
   at::Tensor acc;
   if (!dq16) acc = at::zeros({(int64_t)B * T, D}, qkv.options().dtype(at::kFloat));
-  auto delta = at::empty({B, (int)H, T}, qkv.options().dtype(at::kFloat));
+  at::Tensor delta;
+  if (delta_in.has_value()) {
+    need(delta_in->is_cuda() && delta_in->scalar_type() == at::kFloat && delta_in->is_contiguous() && delta_in->numel() == (int64_t)B * H * T,
+         "attention_bwd: delta must be fp32 contiguous [B, H, T]");
+    delta = *delta_in;
+  } else {
+    delta = at::empty({B, (int)H, T}, qkv.options().dtype(at::kFloat));
+  }
   const float* sl = slopes.has_value() ? slopes->data_ptr<float>() : nullptr;
   const uint64_t* r = rng.has_value() ? (const uint64_t*)rng->data_ptr<int64_t>() : nullptr;
   check(ztb_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr<float>(), dqkv.data_ptr(), dq16 ? nullptr : acc.data_ptr<float>(),
                      delta.data_ptr<float>(), sl, B, T, (int)H, hd, (float)scale, (float)p, r, (uint32_t)op_id, num_sms(), stream(),
-                     dbg.has_value() ? reinterpret_cast<unsigned long long*>(dbg->data_ptr<int64_t>()) : nullptr), "attention_bwd");
+                     dbg.has_value() ? reinterpret_cast<unsigned long long*>(dbg->data_ptr<int64_t>()) : nullptr, delta_in.has_value() ? 1 : 0), "attention_bwd");
   return dqkv;
 }
 
@@ -352,7 +366,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, py::arg("A"), py::arg("B"), py::arg("C") = py::none(), py::arg("epilogue") = 0, py::arg("aux_in") = py::none(),
         py::arg("aux_out") = py::none(), py::arg("p") = 0.0, py::arg("rng") = py::none(), py::arg("op_id") = 0,
         py::arg("accumulate") = false, py::arg("a_mn") = false, py::arg("b_mn") = false, py::arg("two_cta") = false, py::arg("no_split") = false,
-        py::arg("direct_store") = -1, py::arg("raster_n") = -1);
+        py::arg("direct_store") = -1, py::arg("raster_n") = -1, py::arg("rowdot_out") = py::none(), py::arg("rowdot_T") = 0, py::arg("rowdot_hd") = 0);
   m.def("gemm_ag", &gemm_ag, py::arg("A"), py::arg("B"), py::arg("peer_ptrs"), py::arg("local_flat"), py::arg("segs"), py::arg("nseg"),
         py::arg("n_b_segs"), py::arg("total_tiles"), py::arg("shard_ready_ptr"), py::arg("epoch"), py::arg("done"), py::arg("b_tiles_per_rank"),
         py::arg("rows_per_rank"), py::arg("world"), py::arg("rank"), py::arg("two_cta") = false, py::arg("epoch_ptr") = 0);
@@ -363,7 +377,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("segment_struct_size", &segment_struct_size);
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_bwd", &attention_bwd, py::arg("qkv"), py::arg("out"), py::arg("dout"), py::arg("lse"), py::arg("slopes"), py::arg("H"),
-        py::arg("scale"), py::arg("p"), py::arg("rng"), py::arg("op_id"), py::arg("dbg") = py::none(), py::arg("dq_bf16") = false);
+        py::arg("scale"), py::arg("p"), py::arg("rng"), py::arg("op_id"), py::arg("dbg") = py::none(), py::arg("dq_bf16") = false, py::arg("delta") = py::none());
   m.def("signal", &signal, py::arg("pad_ptrs"), py::arg("slot"), py::arg("value"), py::arg("value_ptr") = 0);
   m.def("wait_flags", &wait_flags, py::arg("flags_ptr"), py::arg("n"), py::arg("value"), py::arg("value_ptr") = 0);
   m.def("allgather_pull", &allgather_pull);

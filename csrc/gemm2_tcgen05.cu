@@ -55,6 +55,7 @@ struct GemmParams {
   // 32-column half): bit 0 = the auxiliary output (pre-activation Z), bit 1 = a non-accumulating bf16 C.
   int direct;
   bf16* c_raw; bf16* aux_raw; long long ldc_raw, ld_aux_raw;
+  float* rowdot_out; int rowdot_T, rowdot_hd, rowdot_H;   // ROWDOT epilogue (see ZtbGemmArgs)
   int raster_n;   // 1: walk tiles in groups of GROUP_M column blocks (vocabulary-sized N: the A panel stays in L2)
                   // 2: all row blocks of one column block, column blocks rotated by nb_shift (all-gather variant: the
                   //    column blocks this rank owns come first)
@@ -459,9 +460,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int j = 0; j < 4; ++j)
           if (col + 8 * j < p.N) st_v4(dst + 8 * j, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
       };
+      float rowdot = 0.f;
 #pragma unroll 1
       for (int ci = 0; ci < 2; ++ci) {
-        const int c = chalf + 2 * ci;
+        // ROWDOT: a warp takes two ADJACENT chunks (= one 128-wide head, or two 64-wide heads) so a head's row sum never
+        // leaves the thread; every other epilogue interleaves the two warps of a lane quarter chunk by chunk
+        const int c = EPI == ZTB_EPI_ROWDOT ? chalf * 2 + ci : chalf + 2 * ci;
         const int gcol = n0 + c * 64;
         uint32_t zp[32];   // GELU with a staged auxiliary output: the packed pre-activation waits for the second buffer
         if (!p.c_fp32 && !direct_c) begin_buffer();
@@ -488,6 +492,30 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] = gelu_tanh(v[k]);
+          } else if constexpr (EPI == ZTB_EPI_ROWDOT) {
+            // delta partial: dot of the bf16-ROUNDED output row (what attention backward will read as dO) with aux_in (O)
+            const bool in_rows = grow < p.M;
+            const bf16* ap = p.aux_in + (size_t)grow * p.ld_aux + hcol;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u = make_uint4(0, 0, 0, 0);
+              if (in_rows && hcol + q * 8 < p.N) u = ld_nc_l1_v4(ap + q * 8);
+              uint32_t us[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float2 of = unpack_bf16(us[k]);
+                float2 df = unpack_bf16(pack_bf16(v[q * 8 + 2 * k], v[q * 8 + 2 * k + 1]));
+                rowdot = fmaf(df.x, of.x, fmaf(df.y, of.y, rowdot));
+              }
+            }
+            if (h == 1 && (p.rowdot_hd == 64 || ci == 1)) {   // a head's columns are complete
+              const int head = hcol / p.rowdot_hd;
+              if (in_rows && head < p.rowdot_H) {
+                const int bb = grow / p.rowdot_T, tt = grow - bb * p.rowdot_T;
+                p.rowdot_out[((size_t)bb * p.rowdot_H + head) * p.rowdot_T + tt] = rowdot;
+              }
+              rowdot = 0.f;
+            }
           } else if constexpr (EPI == ZTB_EPI_DROPOUT_ADD || EPI == ZTB_EPI_GELU_BWD) {
             const bool in_rows = grow < p.M;
             const bf16* ap = p.aux_in + (size_t)grow * p.ld_aux + hcol;
@@ -624,7 +652,7 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
   if (g->M <= 0 || g->N <= 0 || g->K <= 0) return 0;
   const int major = (g->a_mn_major ? 2 : 0) | (g->b_mn_major ? 1 : 0);
   const bool supported = g->epilogue == ZTB_EPI_NONE || (major == 0 && (g->epilogue == ZTB_EPI_GELU || g->epilogue == ZTB_EPI_DROPOUT_ADD)) ||
-                         (major == 1 && g->epilogue == ZTB_EPI_GELU_BWD);
+                         (major == 1 && (g->epilogue == ZTB_EPI_GELU_BWD || g->epilogue == ZTB_EPI_ROWDOT));
   if (!supported) return -2;
   if (g->ag != nullptr && (major != 0 || g->epilogue != ZTB_EPI_NONE || g->accumulate || g->c_is_fp32)) {
     ztb_set_error("ztb_gemm_2cta", "all-gather fusion is implemented for the plain K-major forward GEMM", __FILE__, __LINE__);
@@ -656,8 +684,14 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
     rc = ztb_make_tmap_2d(&tx, g->aux_out, 2, g->M, g->N, g->ld_aux, 64, 32);
     if (rc) return rc;
   }
-  if ((g->epilogue == ZTB_EPI_DROPOUT_ADD || g->epilogue == ZTB_EPI_GELU_BWD) && g->aux_in == nullptr) {
+  if ((g->epilogue == ZTB_EPI_DROPOUT_ADD || g->epilogue == ZTB_EPI_GELU_BWD || g->epilogue == ZTB_EPI_ROWDOT) && g->aux_in == nullptr) {
     ztb_set_error("ztb_gemm_2cta", "epilogue needs aux_in", __FILE__, __LINE__); return -1;
+  }
+  p.rowdot_out = g->rowdot_out; p.rowdot_T = g->rowdot_T; p.rowdot_hd = g->rowdot_hd; p.rowdot_H = g->rowdot_hd > 0 ? g->N / g->rowdot_hd : 0;
+  if (g->epilogue == ZTB_EPI_ROWDOT && (g->rowdot_out == nullptr || g->rowdot_T <= 0 || (g->rowdot_hd != 64 && g->rowdot_hd != 128) ||
+                                         g->N % g->rowdot_hd || g->M % g->rowdot_T || g->c_is_fp32 || g->accumulate)) {
+    ztb_set_error("ztb_gemm_2cta", "ROWDOT epilogue: needs rowdot_out, T dividing M, head_dim 64 or 128 dividing N, bf16 non-accumulating C", __FILE__, __LINE__);
+    return -1;
   }
   static const int direct_default = env_int("ZTB_GEMM_DIRECT", 0);
   p.direct = g->direct_store >= 0 ? g->direct_store : direct_default;
@@ -709,14 +743,15 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
   const int units = p.full_tiles + p.tail * p.split;
   if (units < pairs) pairs = units;
   int grid = pairs * 2;
-  switch (major * 4 + g->epilogue) {
-    case 0 * 4 + ZTB_EPI_NONE: return launch2<false, false, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
-    case 0 * 4 + ZTB_EPI_GELU: return launch2<false, false, ZTB_EPI_GELU>(ta, tb, tc, tx, p, grid, st);
-    case 0 * 4 + ZTB_EPI_DROPOUT_ADD: return launch2<false, false, ZTB_EPI_DROPOUT_ADD>(ta, tb, tc, tx, p, grid, st);
-    case 1 * 4 + ZTB_EPI_NONE: return launch2<false, true, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
-    case 1 * 4 + ZTB_EPI_GELU_BWD: return launch2<false, true, ZTB_EPI_GELU_BWD>(ta, tb, tc, tx, p, grid, st);
-    case 2 * 4 + ZTB_EPI_NONE: return launch2<true, false, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
-    case 3 * 4 + ZTB_EPI_NONE: return launch2<true, true, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
+  switch (major * 8 + g->epilogue) {
+    case 0 * 8 + ZTB_EPI_NONE: return launch2<false, false, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
+    case 0 * 8 + ZTB_EPI_GELU: return launch2<false, false, ZTB_EPI_GELU>(ta, tb, tc, tx, p, grid, st);
+    case 0 * 8 + ZTB_EPI_DROPOUT_ADD: return launch2<false, false, ZTB_EPI_DROPOUT_ADD>(ta, tb, tc, tx, p, grid, st);
+    case 1 * 8 + ZTB_EPI_NONE: return launch2<false, true, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
+    case 1 * 8 + ZTB_EPI_GELU_BWD: return launch2<false, true, ZTB_EPI_GELU_BWD>(ta, tb, tc, tx, p, grid, st);
+    case 1 * 8 + ZTB_EPI_ROWDOT: return launch2<false, true, ZTB_EPI_ROWDOT>(ta, tb, tc, tx, p, grid, st);
+    case 2 * 8 + ZTB_EPI_NONE: return launch2<true, false, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
+    case 3 * 8 + ZTB_EPI_NONE: return launch2<true, true, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
   }
   return -2;
 }

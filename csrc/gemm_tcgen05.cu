@@ -445,6 +445,10 @@ int ztb_gemm(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
     const int rc2 = ztb_gemm_2cta(g, sms, st);
     if (rc2 != -2) return rc2;   // -2: that (operand major, epilogue) pair only exists in this general kernel
   }
+  if (g->epilogue == ZTB_EPI_ROWDOT) {
+    ztb_set_error("ztb_gemm", "the ROWDOT epilogue exists only in the CTA-pair kernel (two_cta, dgrad operand major)", __FILE__, __LINE__);
+    return -1;
+  }
   if ((g->lda % 8) || (g->ldb % 8) || (g->ldc % (g->c_is_fp32 ? 4 : 8)) || (g->K % 8) || (g->N % 8)) {
     ztb_set_error("ztb_gemm", "leading dimensions / K / N must be multiples of 8 elements (16-byte TMA strides)", __FILE__, __LINE__);
     return -1;

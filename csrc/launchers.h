@@ -57,7 +57,7 @@ int ztb_adamw_shard(float* master, float* m, float* v, void* flat_param, const v
                     cudaStream_t st);
 
 // ---- gemm_tcgen05.cu
-enum ZtbEpilogue { ZTB_EPI_NONE = 0, ZTB_EPI_GELU = 1, ZTB_EPI_DROPOUT_ADD = 2, ZTB_EPI_GELU_BWD = 3 };
+enum ZtbEpilogue { ZTB_EPI_NONE = 0, ZTB_EPI_GELU = 1, ZTB_EPI_DROPOUT_ADD = 2, ZTB_EPI_GELU_BWD = 3, ZTB_EPI_ROWDOT = 4 };
 struct ZtbAgArgs {              // all-gather fused into the GEMM (see AgParams in gemm_tcgen05.cu)
   const void* peer[8]; void* local;
   const ZtbSegment* segs; int nseg; int n_b_segs; long long total_tiles;
@@ -82,6 +82,9 @@ struct ZtbGemmArgs {
   int no_split;                             // two_cta: disable K-splitting of the last partial wave
   int direct_store;                         // two_cta: -1 default (ZTB_GEMM_DIRECT), else bit 0 aux output / bit 1 C skip smem staging
   int raster_n;                             // two_cta: -1 auto, 0 row-block groups, 1 column-block groups (vocabulary-sized N)
+  // ROWDOT epilogue (two_cta, dgrad major): besides C, emit rowdot_out[b, h, t] = sum over head h's columns of C[m, :] * aux_in[m, :]
+  // for m = b * T + t -- the attention-backward `delta = rowsum(dO o O)` computed where dO is produced.
+  float* rowdot_out; int rowdot_T; int rowdot_hd;
 };
 int ztb_gemm_2cta(const ZtbGemmArgs* args, int sms, cudaStream_t st);
 int ztb_gemm(const ZtbGemmArgs* args, int sms, cudaStream_t st);
@@ -98,6 +101,7 @@ int ztb_p2p_copy(void* dst, const void* src, size_t bytes, int sms, cudaStream_t
 // ---- attention.cu (tcgen05 ALiBi causal flash attention)
 int ztb_attn_fwd(const void* qkv, void* out, float* lse, const float* slopes, int B, int T, int H, int hd, float scale,
                  float dropout_p, const uint64_t* rng, uint32_t op_id, cudaStream_t st);
+// delta_ready != 0: `delta` already holds rowsum(dO o O) (computed by the out-projection dgrad GEMM's ROWDOT epilogue)
 int ztb_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dq_acc, float* delta,
                  const float* slopes, int B, int T, int H, int hd, float scale, float dropout_p, const uint64_t* rng,
-                 uint32_t op_id, int sms, cudaStream_t st, unsigned long long* dbg = nullptr);
+                 uint32_t op_id, int sms, cudaStream_t st, unsigned long long* dbg = nullptr, int delta_ready = 0);

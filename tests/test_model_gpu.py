@@ -330,3 +330,54 @@ def test_chunked_lm_head_loss_matches_unchunked(lazy):
     assert res[0][0] == pytest.approx(res[1][0], rel=1e-3)
     rel = (res[0][1] - res[1][1]).norm() / res[0][1].norm()
     assert rel < 2e-2, rel.item()
+
+
+def test_attention_delta_from_outproj_dgrad_epilogue_matches_standalone_kernel():
+    """rowsum(dO o O) computed in the ROWDOT epilogue of the output projection's dgrad GEMM (no separate kernel) must give
+    the same attention gradients as the standalone delta kernel."""
+    import zero_transformer_b200.ops.cuda as C
+
+    grads = []
+    for fuse in (False, True):
+        C.CONFIG.fuse_attn_delta = fuse
+        try:
+            m, _, cfg = _models(dropout=0.1)
+            C.manual_seed(123)
+            x = torch.randint(0, cfg.vocab_size, (4, 512), device="cuda", dtype=torch.int32)
+            seen = {"n": 0}
+            real = C._C.attention_bwd
+
+            def spy(*a, **k):
+                seen["n"] += int(k.get("delta") is not None)
+                return real(*a, **k)
+
+            C._C.attention_bwd = spy
+            try:
+                m.loss(x, train=True).backward()
+            finally:
+                C._C.attention_bwd = real
+            assert seen["n"] == (cfg.N if fuse else 0)
+            grads.append({n: p.grad.float().clone() for n, p in m.named_parameters()})
+        finally:
+            C.CONFIG.fuse_attn_delta = True
+    for n in grads[0]:
+        rel = (grads[0][n] - grads[1][n]).norm() / (grads[0][n].norm() + 1e-12)
+        assert rel < 2e-3, (n, rel.item())
+
+
+def test_gemm_rowdot_epilogue(K=None):
+    import zero_transformer_b200.ops.cuda as C
+
+    B, T, H, hd = 2, 256, 4, 128
+    M, D = B * T, H * hd
+    dy = (torch.randn(M, D, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(D, D, device="cuda") * 0.05).bfloat16()
+    o = torch.randn(M, D, device="cuda").bfloat16()
+    for hdim in (128, 64):
+        Hh = D // hdim
+        delta = torch.full((B, Hh, T), float("nan"), device="cuda")
+        dx = C._C.gemm(dy, w, b_mn=True, two_cta=True, epilogue=C.EPI_ROWDOT, aux_in=o, rowdot_out=delta, rowdot_T=T, rowdot_hd=hdim)
+        plain = C._C.gemm(dy, w, b_mn=True, two_cta=True)
+        assert torch.equal(dx, plain)
+        want = (dx.float() * o.float()).view(B, T, Hh, hdim).sum(-1).permute(0, 2, 1)
+        torch.testing.assert_close(delta, want, rtol=1e-3, atol=1e-2)

@@ -26,6 +26,7 @@ class _Attention(torch.autograd.Function):
         out, lse = K._C.attention_fwd(qkv, sl, n_head, scale, p, rng if p > 0 else None, op_id)
         ctx.save_for_backward(qkv, out, lse)
         ctx.meta = (sl, n_head, scale, p, op_id)
+        K._note_attention_output(out, n_head, qkv.shape[1])
         return out
 
     @staticmethod
@@ -33,8 +34,12 @@ class _Attention(torch.autograd.Function):
         qkv, out, lse = ctx.saved_tensors
         sl, n_head, scale, p, op_id = ctx.meta
         rng = K.rng_state(qkv.device)
-        dqkv = K._C.attention_bwd(qkv, out, dout.contiguous(), lse, sl, n_head, scale, p, rng if p > 0 else None, op_id,
-                                  dq_bf16=K.CONFIG.attn_dq_bf16)
+        dout = dout.contiguous()
+        delta = K._DELTA_STASH.pop(dout.data_ptr(), None)     # rowsum(dO o O) from the out-projection dgrad GEMM, if it ran fused
+        if delta is not None and tuple(delta.shape) != (qkv.shape[0], n_head, qkv.shape[1]):
+            delta = None
+        dqkv = K._C.attention_bwd(qkv, out, dout, lse, sl, n_head, scale, p, rng if p > 0 else None, op_id,
+                                  dq_bf16=K.CONFIG.attn_dq_bf16, delta=delta)
         return dqkv, None, None, None, None
 
 

@@ -68,7 +68,7 @@ class _Counting:
 
 _C = _Counting(load())
 
-EPI_NONE, EPI_GELU, EPI_DROPOUT_ADD, EPI_GELU_BWD = 0, 1, 2, 3
+EPI_NONE, EPI_GELU, EPI_DROPOUT_ADD, EPI_GELU_BWD, EPI_ROWDOT = 0, 1, 2, 3, 4
 
 
 class _Config:
@@ -85,6 +85,7 @@ class _Config:
     # order-fixed reductions where the fast path uses atomics (LayerNorm weight gradient): bitwise run-to-run
     # reproducibility for T <= 256 (longer sequences: attention dQ has > 2 reduce-add contributions per element)
     deterministic = os.environ.get("ZTB_DETERMINISTIC", "0") == "1"
+    fuse_attn_delta = os.environ.get("ZTB_FUSE_ATTN_DELTA", "1") == "1"   # delta from the out-projection dgrad GEMM's epilogue
     embedding_bwd_sorted = os.environ.get("ZTB_EMB_BWD_SORTED", "1") == "1"  # fp32 per-token sums, one add per gradient row
     fold_dropout_bwd = os.environ.get("ZTB_FOLD_DROPOUT_BWD", "1") == "1"  # LayerNorm-backward emits the masked gradient
 
@@ -220,6 +221,28 @@ def _dropout_bwd(dout2: torch.Tensor, p: float, training: bool, op_id: int, rng:
     return _C.dropout_add(dout2, None, p, rng, op_id)
 
 
+# ---------------------------------------------------------------------------
+# Attention-backward `delta = rowsum(dO o O)` without its own kernel.  dO is produced by the dgrad GEMM of the output
+# projection, whose saved input IS O: that GEMM's ROWDOT epilogue emits delta[b, h, t] from the rows it has in registers
+# (the standalone kernel re-read 2 x 67 MB per layer).  The attention forward leaves a note, the projection that consumes
+# its output picks it up, its backward stashes delta under the address of the dO tensor it returns.
+_LAST_ATTN = {"ptr": 0, "numel": 0, "H": 0, "T": 0}
+_DELTA_STASH = {}
+
+
+def _note_attention_output(out: torch.Tensor, n_head: int, T: int) -> None:
+    if CONFIG.fuse_attn_delta:
+        _LAST_ATTN.update(ptr=out.data_ptr(), numel=out.numel(), H=int(n_head), T=int(T))
+
+
+def _claim_attention_note(x2: torch.Tensor):
+    note = None
+    if _LAST_ATTN["ptr"] and _LAST_ATTN["ptr"] == x2.data_ptr() and _LAST_ATTN["numel"] == x2.numel():
+        note = (_LAST_ATTN["H"], _LAST_ATTN["T"])
+    _LAST_ATTN["ptr"] = 0
+    return note
+
+
 _LN_SCRATCH = {}
 
 
@@ -345,6 +368,7 @@ class _LinearDropoutAdd(torch.autograd.Function):
             out = _C.dropout_add(y, r2.contiguous(), pe, rng, op_id) if y.numel() % 8 == 0 else r2 + y
         ctx.save_for_backward(x2, w)
         ctx.meta = (x.shape, pe, op_id)
+        ctx.attn = _claim_attention_note(x2)      # (heads, T) when x is the output of our attention kernel
         _note_dropout_output(out, pe, op_id)
         return out.view(residual.shape)
 
@@ -356,7 +380,20 @@ class _LinearDropoutAdd(torch.autograd.Function):
         if not d2.is_contiguous():
             d2 = d2.contiguous()
         dy = _dropout_bwd(d2, pe, pe > 0, op_id, rng_state(dout.device))
-        dx = _mm_dgrad(dy, w).view(xshape) if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            M, N = dy.shape
+            Kd = w.shape[1]
+            hd = Kd // ctx.attn[0] if ctx.attn else 0
+            if (ctx.attn and hd in (64, 128) and CONFIG.gemm_2cta and CONFIG.tc_gemm_bwd and _tc_ok(M, Kd, N) and M % 8 == 0
+                    and M % ctx.attn[1] == 0 and max(M, N, Kd) <= 20000):
+                H, T = ctx.attn
+                delta = torch.empty(M // T, H, T, dtype=torch.float32, device=dy.device)
+                dx = _C.gemm(dy, w, b_mn=True, two_cta=True, epilogue=EPI_ROWDOT, aux_in=x2, rowdot_out=delta, rowdot_T=T, rowdot_hd=hd)
+                _DELTA_STASH[dx.data_ptr()] = delta
+                dx = dx.view(xshape)
+            else:
+                dx = _mm_dgrad(dy, w).view(xshape)
         dw = _mm_wgrad(dy, x2, w) if ctx.needs_input_grad[1] else None
         return dx, dw, dout, None, None
 
