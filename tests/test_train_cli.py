@@ -38,3 +38,52 @@ def test_train_resume_export_generate(tmp_path):
     assert len(sd) == 18 * 2 + 4
     model = generate.model_creator("test", str(out), device="cpu")
     assert len(list(generate.generate_from_prompt(model, [5, 6], 4, sample=False))) == 4
+
+
+def _uneven_worker(rank, world, port, root, out):
+    import os
+
+    import numpy as np
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from zero_transformer_b200.config import DEFAULT_MODEL_CFG, load_config
+    from zero_transformer_b200.parallel import dist as pdist
+    from zero_transformer_b200.train import Trainer
+
+    env = pdist.setup_dp(device="cpu")
+    cfg = load_config(None, ["model.size=test", "training.batch_size=4", "training.train_context=16", "data.max_context=32",
+                             "training.gradient_accumulation_steps=1", "training.evaluation_frequency=2", "training.maximum_evaluation_steps=5",
+                             "training.warmup_steps=1", "training.total_steps=50", "training.max_epochs=1", "data.corpus=files",
+                             f"data.bucket_path={root}", f"data.index_path_train={root}/train.index",
+                             f"data.index_path_validation={root}/val.index", "data.shuffle_buffer=1"])
+    tr = Trainer(cfg, DEFAULT_MODEL_CFG, env, log_metrics=False, synthetic=False)
+    last = tr.fit()
+    if rank == 0:
+        import json
+
+        json.dump({"final_step": tr.final_step, "keys": sorted(last)}, open(out, "w"))
+    pdist.shutdown()
+
+
+def test_ranks_stop_together_when_one_runs_out_of_data(tmp_path):
+    """Real shards give ranks different batch counts (striding + drop_last): rank 0 gets 3 train batches, rank 1 only 2; both
+    must leave the loop after 2 steps (and the validation loop after its common prefix) instead of hanging in a collective."""
+    import json
+    import socket
+
+    import numpy as np
+    import torch.multiprocessing as mp
+
+    rng = np.random.default_rng(0)
+    np.save(tmp_path / "a.npy", rng.integers(0, 256, size=(6, 32), dtype=np.int32))   # rank 0: 6 rows -> 3 batches of 2
+    np.save(tmp_path / "b.npy", rng.integers(0, 256, size=(5, 32), dtype=np.int32))   # rank 1: 5 rows -> 2 batches
+    (tmp_path / "train.index").write_text("a.npy\nb.npy\n")
+    np.save(tmp_path / "va.npy", rng.integers(0, 256, size=(2, 32), dtype=np.int32))  # rank 0: 2 validation batches of 1
+    np.save(tmp_path / "vb.npy", rng.integers(0, 256, size=(1, 32), dtype=np.int32))  # rank 1: 1
+    (tmp_path / "val.index").write_text("va.npy\nvb.npy\n")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "res.json")
+    mp.spawn(_uneven_worker, args=(2, port, str(tmp_path), out), nprocs=2, join=True)
+    res = json.load(open(out))
+    assert res["final_step"] == 2 and "validation/loss" in res["keys"]
