@@ -506,6 +506,7 @@ int ztb_layernorm_fwd(const void* x, const void* w, void* y, float* mean, float*
     int nv = D / 256, grid = (M + 3) / 4;
     LN_DISPATCH(nv, layernorm_fwd_kernel, grid, (const bf16*)x, (const bf16*)w, (bf16*)y, mean, rstd, M, eps)
   } else {
+    ztb_prefer_max_smem((const void*)layernorm_fwd_generic);
     layernorm_fwd_generic<<<M, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)y, mean, rstd, M, D, eps);
   }
   ZTB_CUDA_CHECK(cudaGetLastError());
@@ -526,6 +527,7 @@ int ztb_layernorm_bwd(const void* dy, const void* x, const void* w, const float*
     int nv = D / 256, grid = grid_for((M + 3) / 4, 1, sms * 4);
     LN_DISPATCH(nv, layernorm_bwd_kernel, grid, (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, (const bf16*)dres, ex)
   } else {
+    ztb_prefer_max_smem((const void*)layernorm_bwd_generic);
     layernorm_bwd_generic<<<M, 128, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, D, (const bf16*)dres, ex);
   }
   ZTB_CUDA_CHECK(cudaGetLastError());
@@ -554,6 +556,8 @@ int ztb_embedding_fwd(const int* idx, const void* wte, void* out, int M, int D, 
   return 0;
 }
 int ztb_embedding_bwd(const int* idx, const void* dout, void* dwte, int grad_is_fp32, int M, int D, int V, cudaStream_t st) {
+  ztb_prefer_max_smem((const void*)embedding_bwd_kernel<float>);
+  ztb_prefer_max_smem((const void*)embedding_bwd_kernel<bf16>);
   if (grad_is_fp32)
     embedding_bwd_kernel<float><<<(M + 3) / 4, 128, 0, st>>>(idx, (const bf16*)dout, (float*)dwte, M, D, V);
   else
@@ -564,6 +568,8 @@ int ztb_embedding_bwd(const int* idx, const void* dout, void* dwte, int grad_is_
 
 int ztb_embedding_bwd_sorted(const int* sorted_tok, const int* order, const void* dout, void* dwte, int grad_is_fp32, int M, int D, int V,
                              cudaStream_t st) {
+  ztb_prefer_max_smem((const void*)embedding_bwd_sorted_kernel<float>);
+  ztb_prefer_max_smem((const void*)embedding_bwd_sorted_kernel<bf16>);
   if (grad_is_fp32)
     embedding_bwd_sorted_kernel<float><<<(M + 3) / 4, 128, 0, st>>>(sorted_tok, order, (const bf16*)dout, (float*)dwte, M, D, V);
   else
@@ -573,11 +579,13 @@ int ztb_embedding_bwd_sorted(const int* sorted_tok, const int* order, const void
 }
 
 int ztb_gelu_bwd(const void* dg, const void* z, void* dz, size_t n, int sms, cudaStream_t st) {
+  ztb_prefer_max_smem((const void*)gelu_bwd_kernel);
   gelu_bwd_kernel<<<grid_for(n / 8, 256, sms * 8), 256, 0, st>>>((const bf16*)dg, (const bf16*)z, (bf16*)dz, n / 8);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 int ztb_gelu_fwd(const void* z, void* g, size_t n, int sms, cudaStream_t st) {
+  ztb_prefer_max_smem((const void*)gelu_fwd_kernel);
   gelu_fwd_kernel<<<grid_for(n / 8, 256, sms * 8), 256, 0, st>>>((const bf16*)z, (bf16*)g, n / 8);
   ZTB_CUDA_CHECK(cudaGetLastError());
   return 0;

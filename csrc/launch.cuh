@@ -12,7 +12,22 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <unordered_set>
 #include <utility>
+
+// An SM cannot change its L1 / shared-memory split while any CTA is resident.  The background optimizer CTAs and the flag
+// waits live for milliseconds next to the backward pass, whose tcgen05 kernels need the maximum (228 KB) carveout: if
+// such a long-lived CTA lands on an SM that a small kernel left in a small-shared configuration, the next GEMM CTA cannot
+// start there until it exits.  Every kernel of this extension therefore PREFERS the maximum carveout, so the SMs stay in
+// one configuration for the whole step (the cost: 28 KB instead of up to 228 KB of L1 for the streaming elementwise kernels,
+// which do not reuse data anyway).
+inline void ztb_prefer_max_smem(const void* fn) {
+  static std::mutex mu;
+  static std::unordered_set<const void*> done;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.insert(fn).second) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 
 inline bool ztb_pdl_enabled() {
   static int v = -1;
@@ -25,6 +40,7 @@ inline bool ztb_pdl_enabled() {
 
 template <typename... P, typename... A>
 inline cudaError_t ztb_launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  ztb_prefer_max_smem(reinterpret_cast<const void*>(kernel));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
