@@ -78,8 +78,15 @@ ZTB_DEVINL uint32_t bytes_ge(uint32_t w, uint32_t t4) {
   return ((w & ~t4) | (~(w ^ t4) & d)) & H;
 }
 // expand the bit-7 flags of bytes (lo, lo + 1) into a mask over a packed bf16x2 word (PRMT sign-replicate mode)
-ZTB_DEVINL uint32_t pair_mask01(uint32_t flags) { return __byte_perm(flags, 0u, 0x9988u); }
-ZTB_DEVINL uint32_t pair_mask23(uint32_t flags) { return __byte_perm(flags, 0u, 0xbbaau); }
+// (inline PTX: the __byte_perm intrinsic only honours 3 selector bits per nibble; bit 3 = "replicate the selected byte's
+// sign bit" is a feature of the prmt instruction's default mode)
+ZTB_DEVINL uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+ZTB_DEVINL uint32_t pair_mask01(uint32_t flags) { return prmt_b32(flags, 0u, 0x9988u); }
+ZTB_DEVINL uint32_t pair_mask23(uint32_t flags) { return prmt_b32(flags, 0u, 0xbbaau); }
 
 // 16 keep/drop decisions for elements [16*g, 16*g+16) of row `row_id` from one Philox call
 ZTB_DEVINL uint4 attn_dropout_bits(const Philox& ph, uint64_t row_id, uint32_t g, uint64_t stream) {

@@ -87,7 +87,10 @@ class _Config:
     deterministic = os.environ.get("ZTB_DETERMINISTIC", "0") == "1"
     fuse_attn_delta = os.environ.get("ZTB_FUSE_ATTN_DELTA", "1") == "1"   # delta from the out-projection dgrad GEMM's epilogue
     embedding_bwd_sorted = os.environ.get("ZTB_EMB_BWD_SORTED", "1") == "1"  # fp32 per-token sums, one add per gradient row
-    fold_dropout_bwd = os.environ.get("ZTB_FOLD_DROPOUT_BWD", "1") == "1"  # LayerNorm-backward emits the masked gradient
+    # LayerNorm-backward emits the dropout-masked gradient as a second output.  Measured (r2_call1): the Philox work lands in a
+    # kernel that runs 8 warps per SM (64 accumulator registers per thread) and triples its time (56 -> 159 us); the standalone
+    # mask kernel at full occupancy costs 33 us.  Off by default.
+    fold_dropout_bwd = os.environ.get("ZTB_FOLD_DROPOUT_BWD", "0") == "1"
 
 
 CONFIG = _Config()
