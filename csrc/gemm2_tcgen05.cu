@@ -193,7 +193,14 @@ template <bool A_MN, bool B_MN, int EPI, bool AG>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
-                     const GemmParams p, const __grid_constant__ AgParams ag) {
+                     const __grid_constant__ CUtensorMap tmAuxIn, const GemmParams p, const __grid_constant__ AgParams ag) {
+  // Epilogues that read a second operand (residual, pre-activation Z, attention output O) fetch it with per-warp TMA
+  // loads into the warp's first staging buffer.  Round 1 / early round 2 read it with per-thread 16-byte global loads,
+  // one ROW per lane: 32 different cache lines per load instruction = 32 L1 wavefronts each, ~4000 L1/shared-pipeline
+  // cycles per tile on the same SRAM datapath the tensor core reads its operands from (GELU-backward dgrad: 1.05 PFLOP/s
+  // against 1.34 for the same GEMM without the read).  A TMA load costs that pipeline nothing; reading the row back from
+  // swizzled shared memory is 4 conflict-free wavefronts per instruction.
+  constexpr bool kAuxTma = EPI == ZTB_EPI_DROPOUT_ADD || EPI == ZTB_EPI_GELU_BWD || EPI == ZTB_EPI_ROWDOT;
   constexpr int NST = AG ? STAGES_AG : STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -208,8 +215,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]       leader's copy: 8 epilogue warps (both CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   uint64_t* gfull = bars + 2 * STAGES + 5;   // [AG_SLOTS] gather ring: bulk load landed
+  uint64_t* abar = bars + 2 * STAGES + 5 + AG_SLOTS;   // [EPI_WARPS] per-warp "auxiliary operand chunk landed"
   static_assert(AG_SLOTS * AG_TILE_BYTES == STAGE_BYTES, "the gather ring takes exactly one operand stage");
-  static_assert((2 * STAGES + 5 + AG_SLOTS) * 8 <= 256, "barrier block");
+  static_assert((2 * STAGES + 5 + AG_SLOTS + EPI_WARPS) * 8 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -220,11 +228,13 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmC);
     if (p.has_aux_out) prefetch_tmap(&tmAux);
+    if constexpr (kAuxTma) prefetch_tmap(&tmAuxIn);
   }
   if (warp == 9 && lane == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * EPI_WARPS); }
     if constexpr (AG) { for (int i = 0; i < AG_SLOTS; ++i) mbar_init(&gfull[i], 1); }
+    if constexpr (kAuxTma) { for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&abar[i], 1); }
     fence_barrier_init();
   }
   if (warp == 10) {
@@ -403,8 +413,23 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     auto arrive_tempty = [&](int a) { if (leader) mbar_arrive(&tempty[a]); else mbar_arrive_cta0(&tempty[a]); };
     int acc = 0; uint32_t acc_phase = 0;
-    int cbuf = 0;
+    int cbuf = kAuxTma ? 1 : 0;             // aux epilogues: buffer 0 receives the auxiliary operand, buffer 1 stages the output
+    uint32_t aphase = 0;
+    auto chunk_of = [&](int ci) { return EPI == ZTB_EPI_ROWDOT ? chalf * 2 + ci : chalf + 2 * ci; };
+    // TMA load of this warp's 32 x 64 auxiliary chunk for (unit, ci) into buffer 0 (rows / columns outside the tensor arrive
+    // as zeros, so the consumers need no bounds checks)
+    auto issue_aux = [&](const Unit& uu, int ci) {
+      if (lane == 0) {
+        int mb2, nb2; decode_tile(uu.tile, p, mb2, nb2);
+        fence_proxy_async_smem();          // the generic-proxy reads of the previous chunk are complete (syncwarp) before the async write
+        mbar_expect_tx(&abar[e], WBUF_BYTES);
+        tma_load_2d(wbuf, &tmAuxIn, &abar[e], nb2 * BN + chunk_of(ci) * 64, mb2 * TILE_M + (int)cta_rank * BM + ew * 32);
+      }
+    };
     Unit w;
+    if constexpr (kAuxTma) {
+      if (get_unit(pair, p, kblocks, w)) issue_aux(w, 0);
+    }
     for (int u = pair; get_unit(u, p, kblocks, w); u += num_pairs) {
       int mb, nb; decode_tile(w.tile, p, mb, nb);
       const int m0 = mb * TILE_M + cta_rank * BM, n0 = nb * BN;
@@ -431,7 +456,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // reading smem.  Each epilogue warp owns its 32 rows of the staging buffer and issues its own bulk stores
       // ({64|32} x 32-row boxes), so the only synchronisation is warp-local.
       auto begin_buffer = [&]() {
-        if (lane == 0) tma_wait_group_read<1>();
+        if (lane == 0) { if constexpr (kAuxTma) tma_wait_group_read<0>(); else tma_wait_group_read<1>(); }
         __syncwarp();
       };
       auto end_buffer = [&](const CUtensorMap* tm, int col, bool reduce) {
@@ -443,7 +468,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           else tma_store_2d(tm, src, col, m0 + ew * 32);
           tma_commit_group();
         }
-        cbuf ^= 1;
+        if constexpr (!kAuxTma) cbuf ^= 1;
+      };
+      // this thread's 16-byte piece q of half h of its auxiliary row (buffer 0, same 128-byte swizzle as the staging rows)
+      auto aux_piece = [&](int h, int q) {
+        uint4 u;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                     : "r"(smem_u32(wbuf + lane * 128 + (((h * 4 + q) ^ (row & 7)) << 4))));
+        return u;
       };
       // 16 packed bf16x2 words (32 columns) -> half h of this thread's swizzled 128-byte row
       auto stage_packed_half = [&](const uint32_t* pk, int h) {
@@ -465,8 +497,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int ci = 0; ci < 2; ++ci) {
         // ROWDOT: a warp takes two ADJACENT chunks (= one 128-wide head, or two 64-wide heads) so a head's row sum never
         // leaves the thread; every other epilogue interleaves the two warps of a lane quarter chunk by chunk
-        const int c = EPI == ZTB_EPI_ROWDOT ? chalf * 2 + ci : chalf + 2 * ci;
+        const int c = chunk_of(ci);
         const int gcol = n0 + c * 64;
+        if constexpr (kAuxTma) { mbar_wait(&abar[e], aphase); aphase ^= 1; }
         uint32_t zp[32];   // GELU with a staged auxiliary output: the packed pre-activation waits for the second buffer
         if (!p.c_fp32 && !direct_c) begin_buffer();
 #pragma unroll
@@ -495,11 +528,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           } else if constexpr (EPI == ZTB_EPI_ROWDOT) {
             // delta partial: dot of the bf16-ROUNDED output row (what attention backward will read as dO) with aux_in (O)
             const bool in_rows = grow < p.M;
-            const bf16* ap = p.aux_in + (size_t)grow * p.ld_aux + hcol;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              uint4 u = make_uint4(0, 0, 0, 0);
-              if (in_rows && hcol + q * 8 < p.N) u = ld_nc_l1_v4(ap + q * 8);
+              const uint4 u = aux_piece(h, q);
               uint32_t us[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -517,14 +548,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               rowdot = 0.f;
             }
           } else if constexpr (EPI == ZTB_EPI_DROPOUT_ADD || EPI == ZTB_EPI_GELU_BWD) {
-            const bool in_rows = grow < p.M;
-            const bf16* ap = p.aux_in + (size_t)grow * p.ld_aux + hcol;
             uint4 au[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              au[q] = make_uint4(0, 0, 0, 0);
-              if (in_rows && hcol + q * 8 < p.N) au[q] = ld_nc_l1_v4(ap + q * 8);
-            }
+            for (int q = 0; q < 4; ++q) au[q] = aux_piece(h, q);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint32_t us[4] = {au[q].x, au[q].y, au[q].z, au[q].w};
@@ -565,6 +591,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (direct_c) store_direct_half(p.c_raw, p.ldc_raw, pk, hcol);
             else stage_packed_half(pk, h);
           }
+        }
+        if constexpr (kAuxTma) {
+          __syncwarp();                    // every lane has consumed its auxiliary row: buffer 0 may be refilled
+          Unit wn;
+          if (ci == 0) issue_aux(w, 1);
+          else if (get_unit(u + num_pairs, p, kblocks, wn)) issue_aux(wn, 0);
         }
         if (!p.c_fp32 && !direct_c) end_buffer(&tmC, gcol, reduce_c);
         if constexpr (EPI == ZTB_EPI_GELU) {
@@ -607,8 +639,8 @@ int ztb_make_tmap_2d(CUtensorMap* tm, const void* ptr, int elem_bytes, long long
                      int box_cols, int box_rows);
 
 template <bool A_MN, bool B_MN, int EPI, bool AG = false>
-static int launch2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& x, const g2::GemmParams& p,
-                   int grid, cudaStream_t st, const g2::AgParams* agp = nullptr) {
+static int launch2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& x, const CUtensorMap& xin,
+                   const g2::GemmParams& p, int grid, cudaStream_t st, const g2::AgParams* agp = nullptr) {
   auto kern = g2::gemm2_tcgen05_kernel<A_MN, B_MN, EPI, AG>;
   static bool configured = false;
   if (!configured) {
@@ -617,7 +649,7 @@ static int launch2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap
   }
   g2::AgParams ag{};
   if (agp) ag = *agp;
-  ZTB_CUDA_CHECK(ztb_launch(kern, dim3(grid), dim3(g2::GEMM_THREADS), g2::GEMM_SMEM, st, a, b, c, x, p, ag));  // cluster dims are compile-time (2,1,1)
+  ZTB_CUDA_CHECK(ztb_launch(kern, dim3(grid), dim3(g2::GEMM_THREADS), g2::GEMM_SMEM, st, a, b, c, x, xin, p, ag));  // cluster dims are compile-time (2,1,1)
   return 0;
 }
 
@@ -674,6 +706,12 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
                     : ztb_make_tmap_2d(&tc, g->C, 2, g->M, g->N, g->ldc, 64, 32);
   if (rc) return rc;
   tx = tc;
+  CUtensorMap tin = tc;   // auxiliary INPUT operand (residual / Z / O): 64-column x 32-row boxes, one per epilogue warp and chunk
+  if (g->aux_in != nullptr && (g->epilogue == ZTB_EPI_DROPOUT_ADD || g->epilogue == ZTB_EPI_GELU_BWD || g->epilogue == ZTB_EPI_ROWDOT)) {
+    if (g->ld_aux % 8) { ztb_set_error("ztb_gemm_2cta", "aux_in row stride must be a multiple of 8 elements", __FILE__, __LINE__); return -1; }
+    rc = ztb_make_tmap_2d(&tin, g->aux_in, 2, g->M, g->N, g->ld_aux, 64, 32);
+    if (rc) return rc;
+  }
   GemmParams p;
   p.M = g->M; p.N = g->N; p.K = g->K;
   p.epi = g->epilogue; p.c_fp32 = g->c_is_fp32; p.accumulate = g->accumulate;
@@ -725,7 +763,7 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
     p.raster_n = 2;
     p.nb_shift = ((a->rank * a->rows_per_rank) / BN) % p.tiles_n;
     p.full_tiles = p.num_tiles; p.tail = 0; p.split = 1; p.chain = nullptr; p.direct = 0;
-    return launch2<false, false, ZTB_EPI_NONE, true>(ta, tb, tc, tx, p, pairs * 2, st, &ag);
+    return launch2<false, false, ZTB_EPI_NONE, true>(ta, tb, tc, tx, tin, p, pairs * 2, st, &ag);
   }
   if (p.tail > 0 && g->epilogue == ZTB_EPI_NONE && !g->no_split) {
     float best = 1.f;
@@ -744,14 +782,14 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
   if (units < pairs) pairs = units;
   int grid = pairs * 2;
   switch (major * 8 + g->epilogue) {
-    case 0 * 8 + ZTB_EPI_NONE: return launch2<false, false, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
-    case 0 * 8 + ZTB_EPI_GELU: return launch2<false, false, ZTB_EPI_GELU>(ta, tb, tc, tx, p, grid, st);
-    case 0 * 8 + ZTB_EPI_DROPOUT_ADD: return launch2<false, false, ZTB_EPI_DROPOUT_ADD>(ta, tb, tc, tx, p, grid, st);
-    case 1 * 8 + ZTB_EPI_NONE: return launch2<false, true, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
-    case 1 * 8 + ZTB_EPI_GELU_BWD: return launch2<false, true, ZTB_EPI_GELU_BWD>(ta, tb, tc, tx, p, grid, st);
-    case 1 * 8 + ZTB_EPI_ROWDOT: return launch2<false, true, ZTB_EPI_ROWDOT>(ta, tb, tc, tx, p, grid, st);
-    case 2 * 8 + ZTB_EPI_NONE: return launch2<true, false, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
-    case 3 * 8 + ZTB_EPI_NONE: return launch2<true, true, ZTB_EPI_NONE>(ta, tb, tc, tx, p, grid, st);
+    case 0 * 8 + ZTB_EPI_NONE: return launch2<false, false, ZTB_EPI_NONE>(ta, tb, tc, tx, tin, p, grid, st);
+    case 0 * 8 + ZTB_EPI_GELU: return launch2<false, false, ZTB_EPI_GELU>(ta, tb, tc, tx, tin, p, grid, st);
+    case 0 * 8 + ZTB_EPI_DROPOUT_ADD: return launch2<false, false, ZTB_EPI_DROPOUT_ADD>(ta, tb, tc, tx, tin, p, grid, st);
+    case 1 * 8 + ZTB_EPI_NONE: return launch2<false, true, ZTB_EPI_NONE>(ta, tb, tc, tx, tin, p, grid, st);
+    case 1 * 8 + ZTB_EPI_GELU_BWD: return launch2<false, true, ZTB_EPI_GELU_BWD>(ta, tb, tc, tx, tin, p, grid, st);
+    case 1 * 8 + ZTB_EPI_ROWDOT: return launch2<false, true, ZTB_EPI_ROWDOT>(ta, tb, tc, tx, tin, p, grid, st);
+    case 2 * 8 + ZTB_EPI_NONE: return launch2<true, false, ZTB_EPI_NONE>(ta, tb, tc, tx, tin, p, grid, st);
+    case 3 * 8 + ZTB_EPI_NONE: return launch2<true, true, ZTB_EPI_NONE>(ta, tb, tc, tx, tin, p, grid, st);
   }
   return -2;
 }
