@@ -44,7 +44,8 @@ std::vector<at::Tensor> layernorm_bwd(const at::Tensor& dy, const at::Tensor& x,
                                       const at::Tensor& rstd, const c10::optional<at::Tensor>& dres,
                                       const c10::optional<at::Tensor>& grad_out, bool accumulate,
                                       const c10::optional<at::Tensor>& scratch, const c10::optional<at::Tensor>& ticket,
-                                      double drop_p, const c10::optional<at::Tensor>& rng, int64_t op_id, bool deterministic) {
+                                      double drop_p, const c10::optional<at::Tensor>& rng, int64_t op_id, bool deterministic,
+                                      const c10::optional<at::Tensor>& drop_mask) {
   need(is_bf16_cuda(dy) && is_bf16_cuda(x) && dy.is_contiguous() && x.is_contiguous(), "layernorm_bwd: bf16 contiguous");
   c10::cuda::CUDAGuard g(x.device());
   int D = x.size(-1);
@@ -74,9 +75,16 @@ std::vector<at::Tensor> layernorm_bwd(const at::Tensor& dy, const at::Tensor& x,
     dwp = dw.data_ptr<float>();
   }
   if (drop_p > 0.0) {
-    need(rng.has_value() && rng->is_cuda() && rng->scalar_type() == at::kLong && rng->numel() >= 2, "layernorm_bwd: dropout output needs rng (CUDA int64[2])");
     dmask = at::empty_like(x);
-    ex.dmask = dmask.data_ptr(); ex.p = (float)drop_p; ex.rng = (const uint64_t*)rng->data_ptr<int64_t>(); ex.op_id = (uint32_t)op_id;
+    ex.dmask = dmask.data_ptr(); ex.p = (float)drop_p; ex.op_id = (uint32_t)op_id;
+    if (drop_mask.has_value()) {
+      need(drop_mask->is_cuda() && drop_mask->is_contiguous() && drop_mask->element_size() == 4 && D % 32 == 0 &&
+           drop_mask->numel() == (int64_t)M * (D / 32), "layernorm_bwd: drop_mask must be the contiguous 32-bit [M, D/32] keep-bit tensor of the forward epilogue");
+      ex.maskbits = reinterpret_cast<const unsigned char*>(drop_mask->data_ptr());
+    } else {
+      need(rng.has_value() && rng->is_cuda() && rng->scalar_type() == at::kLong && rng->numel() >= 2, "layernorm_bwd: dropout output needs rng (CUDA int64[2]) or drop_mask");
+      ex.rng = (const uint64_t*)rng->data_ptr<int64_t>();
+    }
   } else {
     dmask = at::empty({0}, x.options());
   }
@@ -165,7 +173,8 @@ void ce_bwd_(at::Tensor& logits, const at::Tensor& labels, const at::Tensor& lse
 at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tensor> C_, int64_t epilogue,
                 const c10::optional<at::Tensor>& aux_in, c10::optional<at::Tensor> aux_out, double p,
                 const c10::optional<at::Tensor>& rng, int64_t op_id, bool accumulate, bool a_mn, bool b_mn, bool two_cta, bool no_split,
-                int64_t direct_store, int64_t raster_n, c10::optional<at::Tensor> rowdot_out, int64_t rowdot_T, int64_t rowdot_hd) {
+                int64_t direct_store, int64_t raster_n, c10::optional<at::Tensor> rowdot_out, int64_t rowdot_T, int64_t rowdot_hd,
+                c10::optional<at::Tensor> mask_out) {
   need(is_bf16_cuda(A) && is_bf16_cuda(B) && A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "gemm: A, B must be 2-D bf16 CUDA with unit inner stride");
   c10::cuda::CUDAGuard g(A.device());
   ZtbGemmArgs a{};
@@ -208,6 +217,11 @@ at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tens
     a.rowdot_out = rowdot_out->data_ptr<float>(); a.rowdot_T = (int)rowdot_T; a.rowdot_hd = (int)rowdot_hd;
   }
   need(epilogue != ZTB_EPI_ROWDOT || (a.rowdot_out != nullptr && two_cta), "gemm: ROWDOT epilogue needs rowdot_out and two_cta");
+  if (mask_out.has_value()) {
+    need(two_cta && epilogue == ZTB_EPI_DROPOUT_ADD && a.N % 32 == 0 && mask_out->is_cuda() && mask_out->is_contiguous() && mask_out->element_size() == 4 &&
+         mask_out->numel() == (int64_t)a.M * (a.N / 32), "gemm: mask_out must be a contiguous 32-bit [M, N/32] CUDA tensor (two_cta, dropout epilogue, N % 32 == 0)");
+    a.mask_out = reinterpret_cast<unsigned int*>(mask_out->data_ptr());
+  }
   check(ztb_gemm(&a, num_sms(), stream()), "gemm");
   return C;
 }
@@ -354,7 +368,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("layernorm_fwd", &layernorm_fwd);
   m.def("layernorm_bwd", &layernorm_bwd, py::arg("dy"), py::arg("x"), py::arg("w"), py::arg("mean"), py::arg("rstd"), py::arg("dres") = py::none(),
         py::arg("grad_out") = py::none(), py::arg("accumulate") = false, py::arg("scratch") = py::none(), py::arg("ticket") = py::none(),
-        py::arg("drop_p") = 0.0, py::arg("rng") = py::none(), py::arg("op_id") = 0, py::arg("deterministic") = false);
+        py::arg("drop_p") = 0.0, py::arg("rng") = py::none(), py::arg("op_id") = 0, py::arg("deterministic") = false, py::arg("drop_mask") = py::none());
   m.def("dropout_add", &dropout_add);
   m.def("embedding_fwd", &embedding_fwd);
   m.def("embedding_bwd_", &embedding_bwd_);
@@ -366,7 +380,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, py::arg("A"), py::arg("B"), py::arg("C") = py::none(), py::arg("epilogue") = 0, py::arg("aux_in") = py::none(),
         py::arg("aux_out") = py::none(), py::arg("p") = 0.0, py::arg("rng") = py::none(), py::arg("op_id") = 0,
         py::arg("accumulate") = false, py::arg("a_mn") = false, py::arg("b_mn") = false, py::arg("two_cta") = false, py::arg("no_split") = false,
-        py::arg("direct_store") = -1, py::arg("raster_n") = -1, py::arg("rowdot_out") = py::none(), py::arg("rowdot_T") = 0, py::arg("rowdot_hd") = 0);
+        py::arg("direct_store") = -1, py::arg("raster_n") = -1, py::arg("rowdot_out") = py::none(), py::arg("rowdot_T") = 0, py::arg("rowdot_hd") = 0, py::arg("mask_out") = py::none());
   m.def("gemm_ag", &gemm_ag, py::arg("A"), py::arg("B"), py::arg("peer_ptrs"), py::arg("local_flat"), py::arg("segs"), py::arg("nseg"),
         py::arg("n_b_segs"), py::arg("total_tiles"), py::arg("shard_ready_ptr"), py::arg("epoch"), py::arg("done"), py::arg("b_tiles_per_rank"),
         py::arg("rows_per_rank"), py::arg("world"), py::arg("rank"), py::arg("two_cta") = false, py::arg("epoch_ptr") = 0);

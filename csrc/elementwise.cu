@@ -74,6 +74,7 @@ struct LnBwdExtra {
   float* partials;       // optional [gridDim.x, D]: deterministic mode -- per-block partial sums, added up in block order by
                          // the last block instead of meeting through fp32 atomics (whose order changes run to run)
   bf16* dmask;           // optional [M, D]
+  const unsigned char* maskbits;   // optional [M, D / 8] keep bits from the forward epilogue (else the mask is regenerated with Philox)
   float p, inv_keep;
   const uint64_t* rng;
   uint32_t op_id;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
   uint64_t stream = 0;
   uint32_t thr = 0;
   Philox ph(0);
-  if (drop) { ph = Philox(ex.rng[0]); stream = ex.rng[1] * 65536ull + ex.op_id; thr = dropout_threshold(ex.p); }
+  if (drop && ex.maskbits == nullptr) { ph = Philox(ex.rng[0]); stream = ex.rng[1] * 65536ull + ex.op_id; thr = dropout_threshold(ex.p); }
   for (int row = blockIdx.x * 4 + warp; row < M; row += gridDim.x * 4) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * D);
     const uint4* gr = reinterpret_cast<const uint4*>(dy + (size_t)row * D);
@@ -171,12 +172,20 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
       st_v4(dr + i * 32 + lane, make_uint4(os[0], os[1], os[2], os[3]));
       if (drop) {  // masked copy of the (bf16-rounded) dx, exactly what dropout_add_kernel<false> would produce from it
         const size_t vi = (size_t)row * (D / 8) + i * 32 + lane;
-        uint4 r0 = ph.rounds<kPhiloxRounds>(2 * vi, stream), r1 = ph.rounds<kPhiloxRounds>(2 * vi + 1, stream);
-        uint32_t rb[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w}, ms[4];
+        uint32_t keep8, ms[4];
+        if (ex.maskbits != nullptr) {
+          keep8 = ex.maskbits[vi];           // 8 keep bits recorded by the forward GEMM epilogue: no RNG work here
+        } else {
+          uint4 r0 = ph.rounds<kPhiloxRounds>(2 * vi, stream), r1 = ph.rounds<kPhiloxRounds>(2 * vi + 1, stream);
+          uint32_t rb[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          keep8 = 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) keep8 |= (rb[k] >= thr ? 1u : 0u) << k;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           float2 df = unpack_bf16(os[k]);
-          ms[k] = pack_bf16(rb[2 * k] >= thr ? df.x * ex.inv_keep : 0.f, rb[2 * k + 1] >= thr ? df.y * ex.inv_keep : 0.f);
+          ms[k] = pack_bf16((keep8 >> (2 * k)) & 1u ? df.x * ex.inv_keep : 0.f, (keep8 >> (2 * k + 1)) & 1u ? df.y * ex.inv_keep : 0.f);
         }
         st_v4(reinterpret_cast<uint4*>(ex.dmask + (size_t)row * D) + i * 32 + lane, make_uint4(ms[0], ms[1], ms[2], ms[3]));
       }
@@ -243,10 +252,16 @@ __global__ void layernorm_bwd_generic(const bf16* __restrict__ dy, const bf16* _
     dx[(size_t)row * D + c] = o;
     if (ex.dmask != nullptr) {   // same mask as dropout_add_kernel: element e -> Philox counter e / 4, word e % 4
       const size_t e = (size_t)row * D + c;
-      Philox ph(ex.rng[0]);
-      uint4 r4 = ph.rounds<kPhiloxRounds>(e >> 2, ex.rng[1] * 65536ull + ex.op_id);
-      uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-      ex.dmask[e] = __float2bfloat16(rw[e & 3] >= dropout_threshold(ex.p) ? __bfloat162float(o) * ex.inv_keep : 0.f);
+      bool keep;
+      if (ex.maskbits != nullptr) {
+        keep = (ex.maskbits[e >> 3] >> (e & 7)) & 1u;
+      } else {
+        Philox ph(ex.rng[0]);
+        uint4 r4 = ph.rounds<kPhiloxRounds>(e >> 2, ex.rng[1] * 65536ull + ex.op_id);
+        uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+        keep = rw[e & 3] >= dropout_threshold(ex.p);
+      }
+      ex.dmask[e] = __float2bfloat16(keep ? __bfloat162float(o) * ex.inv_keep : 0.f);
     }
   }
   ln_bwd_finalize(dw, D, ex, &is_last);
@@ -521,6 +536,7 @@ int ztb_layernorm_bwd(const void* dy, const void* x, const void* w, const float*
     ex.ticket = extra->ticket; ex.dmask = (bf16*)extra->dmask; ex.p = extra->p;
     ex.partials = ln_fast(D) ? extra->partials : nullptr;   // the generic (odd-D) kernel keeps its per-element atomics
     ex.inv_keep = extra->p < 1.f ? 1.f / (1.f - extra->p) : 0.f; ex.rng = extra->rng; ex.op_id = extra->op_id;
+    ex.maskbits = extra->maskbits;
   }
   if (ex.ticket == nullptr) ZTB_CUDA_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * D, st));   // one-shot scratch: caller owns dw
   if (ln_fast(D)) {

@@ -56,6 +56,7 @@ struct GemmParams {
   int direct;
   bf16* c_raw; bf16* aux_raw; long long ldc_raw, ld_aux_raw;
   float* rowdot_out; int rowdot_T, rowdot_hd, rowdot_H;   // ROWDOT epilogue (see ZtbGemmArgs)
+  unsigned int* mask_out; int mask_ld;                     // DROPOUT_ADD: keep bits, mask_ld = words per row
   int raster_n;   // 1: walk tiles in groups of GROUP_M column blocks (vocabulary-sized N: the A panel stays in L2)
                   // 2: all row blocks of one column block, column blocks rotated by nb_shift (all-gather variant: the
                   //    column blocks this rank owns come first)
@@ -549,6 +550,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
           } else if constexpr (EPI == ZTB_EPI_DROPOUT_ADD || EPI == ZTB_EPI_GELU_BWD) {
             uint4 au[4];
+            uint32_t keep_bits = 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) au[q] = aux_piece(h, q);
 #pragma unroll
@@ -561,8 +563,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   float2 rf = unpack_bf16(us[k]);
-                  float a = rr[2 * k] >= thr ? v[q * 8 + 2 * k] * p.inv_keep : 0.f;
-                  float b = rr[2 * k + 1] >= thr ? v[q * 8 + 2 * k + 1] * p.inv_keep : 0.f;
+                  const bool k0 = rr[2 * k] >= thr, k1 = rr[2 * k + 1] >= thr;
+                  keep_bits |= (k0 ? 1u : 0u) << (q * 8 + 2 * k) | (k1 ? 1u : 0u) << (q * 8 + 2 * k + 1);
+                  float a = k0 ? v[q * 8 + 2 * k] * p.inv_keep : 0.f;
+                  float b = k1 ? v[q * 8 + 2 * k + 1] * p.inv_keep : 0.f;
                   v[q * 8 + 2 * k] = rf.x + a;
                   v[q * 8 + 2 * k + 1] = rf.y + b;
                 }
@@ -574,6 +578,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                   v[q * 8 + 2 * k + 1] *= gelu_tanh_grad(zf.y);
                 }
               }
+            }
+            if constexpr (EPI == ZTB_EPI_DROPOUT_ADD) {
+              if (p.mask_out != nullptr && grow < p.M && hcol < p.N) p.mask_out[(size_t)grow * p.mask_ld + (hcol >> 5)] = keep_bits;
             }
           }
           if (p.c_fp32) {   // 32 fp32 columns fill a 128-byte row: one buffer and one bulk store per half
@@ -725,6 +732,8 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
   if ((g->epilogue == ZTB_EPI_DROPOUT_ADD || g->epilogue == ZTB_EPI_GELU_BWD || g->epilogue == ZTB_EPI_ROWDOT) && g->aux_in == nullptr) {
     ztb_set_error("ztb_gemm_2cta", "epilogue needs aux_in", __FILE__, __LINE__); return -1;
   }
+  p.mask_out = g->epilogue == ZTB_EPI_DROPOUT_ADD ? g->mask_out : nullptr; p.mask_ld = g->N / 32;
+  if (p.mask_out != nullptr && g->N % 32) { ztb_set_error("ztb_gemm_2cta", "mask_out needs N % 32 == 0", __FILE__, __LINE__); return -1; }
   p.rowdot_out = g->rowdot_out; p.rowdot_T = g->rowdot_T; p.rowdot_hd = g->rowdot_hd; p.rowdot_H = g->rowdot_hd > 0 ? g->N / g->rowdot_hd : 0;
   if (g->epilogue == ZTB_EPI_ROWDOT && (g->rowdot_out == nullptr || g->rowdot_T <= 0 || (g->rowdot_hd != 64 && g->rowdot_hd != 128) ||
                                          g->N % g->rowdot_hd || g->M % g->rowdot_T || g->c_is_fp32 || g->accumulate)) {

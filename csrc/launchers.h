@@ -17,6 +17,7 @@ struct ZtbLnBwdExtra {
   void* grad_out; int grad_fp32; int grad_accumulate; unsigned int* ticket;
   float* partials;   // optional [ztb_layernorm_bwd_grid(M, D, sms), D]: order-fixed (bitwise reproducible) weight-gradient reduction
   void* dmask; float p; const uint64_t* rng; uint32_t op_id;
+  const unsigned char* maskbits;   // optional [M, D / 8]: keep bits recorded by the forward GEMM epilogue; replaces the Philox recomputation
 };
 int ztb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
                       float* dw, int M, int D, int sms, cudaStream_t st, const void* dres = nullptr,
@@ -85,6 +86,9 @@ struct ZtbGemmArgs {
   // ROWDOT epilogue (two_cta, dgrad major): besides C, emit rowdot_out[b, h, t] = sum over head h's columns of C[m, :] * aux_in[m, :]
   // for m = b * T + t -- the attention-backward `delta = rowsum(dO o O)` computed where dO is produced.
   float* rowdot_out; int rowdot_T; int rowdot_hd;
+  // DROPOUT_ADD epilogue (two_cta): optionally record the keep decisions, 1 bit per output element, row-major, (N / 32) 32-bit
+  // words per row (bit k of word w of row m <-> column 32 w + k) -- backward then needs no Philox recomputation.
+  unsigned int* mask_out;
 };
 int ztb_gemm_2cta(const ZtbGemmArgs* args, int sms, cudaStream_t st);
 int ztb_gemm(const ZtbGemmArgs* args, int sms, cudaStream_t st);

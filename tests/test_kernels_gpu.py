@@ -422,8 +422,16 @@ def test_dropout_backward_is_served_by_layernorm_backward(K, monkeypatch):
         monkeypatch.setattr(C._C, "dropout_add", real)
         return calls["n"], [t.grad.clone() for t in (x, w, lnw, res)]
 
-    n_fold, g_fold = run(True)
+    monkeypatch.setattr(C.CONFIG, "fold_dropout_philox", False)
+    n_fold, g_fold = run(True)            # keep bits from the forward epilogue
     n_plain, g_plain = run(False)
+    monkeypatch.setattr(C.CONFIG, "fold_dropout_philox", True)
+    monkeypatch.setattr(C.CONFIG, "gemm_2cta", False)
+    n_phil, g_phil = run(True)            # no bits available (1-CTA GEMM): mask regenerated inside LayerNorm backward
+    monkeypatch.setattr(C.CONFIG, "gemm_2cta", True)
+    assert n_phil == 0
+    for a, b in zip(g_phil, g_plain):
+        assert torch.equal(a, b)
     assert n_fold == 0 and n_plain == 1
     for a, b in zip(g_fold, g_plain):
         assert torch.equal(a, b)
@@ -494,3 +502,29 @@ def test_attention_bwd_bf16_dq_accumulation(K, B, T, H):
     ro.backward(dout.float())
     relr = (g16[..., :D].float() - q2.grad[..., :D]).norm() / q2.grad[..., :D].norm()
     assert relr < 2e-2, relr.item()
+
+
+def test_gemm_dropout_epilogue_records_keep_bits(K):
+    """The dropout+residual epilogue writes 1 keep bit per output element; LayerNorm backward fed those bits must produce
+    the same masked gradient as the standalone Philox kernel."""
+    M, N, Kd = 520, 1024, 256
+    a, b, res = _rand(M, Kd), _rand(N, Kd, scale=0.05), _rand(M, N)
+    rng = K.rng_state("cuda")
+    p = 0.3
+    mask = torch.zeros(M, N // 32, dtype=torch.int32, device="cuda")
+    out = K._C.gemm(a, b, epilogue=K.EPI_DROPOUT_ADD, aux_in=res, p=p, rng=rng, op_id=9, two_cta=True, mask_out=mask)
+    out0 = K._C.gemm(a, b, epilogue=K.EPI_DROPOUT_ADD, aux_in=res, p=p, rng=rng, op_id=9, two_cta=True)
+    assert torch.equal(out, out0)
+    bits = ((mask.view(torch.uint8).view(M, N // 8, 1) >> torch.arange(8, device="cuda", dtype=torch.uint8).view(1, 1, 8)) & 1).reshape(M, N).bool()
+    ones = torch.ones(M, N, dtype=torch.bfloat16, device="cuda")
+    ref_keep = K._C.dropout_add(ones, None, p, rng, 9) != 0          # same (seed, offset, op id) -> the mask the epilogue used
+    assert torch.equal(bits, ref_keep)
+    assert abs(bits.float().mean().item() - (1 - p)) < 0.02
+    # LayerNorm backward consuming the bits
+    D = N
+    x, dy = _rand(M, D), _rand(M, D)
+    w = torch.ones(D, device="cuda", dtype=torch.bfloat16)
+    _, mean, rstd = K._C.layernorm_fwd(x, w, 1e-5)
+    dx, _, dm = K._C.layernorm_bwd(dy, x, w, mean, rstd, None, drop_p=p, op_id=9, drop_mask=mask)
+    want = K._C.dropout_add(dx, None, p, rng, 9)
+    assert torch.equal(dm, want)

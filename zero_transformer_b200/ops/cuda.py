@@ -87,10 +87,12 @@ class _Config:
     deterministic = os.environ.get("ZTB_DETERMINISTIC", "0") == "1"
     fuse_attn_delta = os.environ.get("ZTB_FUSE_ATTN_DELTA", "1") == "1"   # delta from the out-projection dgrad GEMM's epilogue
     embedding_bwd_sorted = os.environ.get("ZTB_EMB_BWD_SORTED", "1") == "1"  # fp32 per-token sums, one add per gradient row
-    # LayerNorm-backward emits the dropout-masked gradient as a second output.  Measured (r2_call1): the Philox work lands in a
-    # kernel that runs 8 warps per SM (64 accumulator registers per thread) and triples its time (56 -> 159 us); the standalone
-    # mask kernel at full occupancy costs 33 us.  Off by default.
-    fold_dropout_bwd = os.environ.get("ZTB_FOLD_DROPOUT_BWD", "0") == "1"
+    # LayerNorm-backward emits the dropout-masked gradient as a second output (one extra store instead of a read + write +
+    # launch).  The keep decisions come as 1 bit per element from the forward GEMM epilogue, which computes them anyway.
+    # (First version regenerated them with Philox inside LayerNorm backward -- a kernel that runs 8 warps per SM because of its
+    # 64 accumulator registers: 56 -> 159 us per call, measured in r2 call 1; that variant is `fold_dropout_philox`, off.)
+    fold_dropout_bwd = os.environ.get("ZTB_FOLD_DROPOUT_BWD", "1") == "1"
+    fold_dropout_philox = os.environ.get("ZTB_FOLD_DROPOUT_PHILOX", "0") == "1"
 
 
 CONFIG = _Config()
@@ -198,20 +200,29 @@ def _mm_wgrad(dy: torch.Tensor, x2: torch.Tensor, w: torch.Tensor) -> Optional[t
 # dgrad / wgrad GEMMs need.  The LayerNorm-backward kernel therefore emits mask(dx) / keep as a second output
 # (one extra store instead of a read + write + launch): the forward op leaves a note (``_LAST_DROP``), the LayerNorm
 # forward that consumes the tensor picks it up, its backward stashes the masked gradient under the op id.
-_LAST_DROP = {"ptr": 0, "numel": 0, "p": 0.0, "op_id": 0}
+_LAST_DROP = {"ptr": 0, "numel": 0, "p": 0.0, "op_id": 0, "mask": None}
 _DROP_STASH = {}
 
 
-def _note_dropout_output(out: torch.Tensor, p: float, op_id: int) -> None:
-    if p > 0.0 and CONFIG.fold_dropout_bwd:
-        _LAST_DROP.update(ptr=out.data_ptr(), numel=out.numel(), p=float(p), op_id=int(op_id))
+def _new_keep_mask(M: int, N: int, device, p: float):
+    """(M, N/32) int32 buffer for the keep bits the dropout GEMM epilogue records (1 bit per output element), or None
+    when the backward mask will not be folded into LayerNorm backward anyway."""
+    if p > 0.0 and CONFIG.fold_dropout_bwd and CONFIG.gemm_2cta and N % 32 == 0 and max(M, N) <= 20000:
+        return torch.empty(M, N // 32, dtype=torch.int32, device=device)
+    return None
+
+
+def _note_dropout_output(out: torch.Tensor, p: float, op_id: int, mask: Optional[torch.Tensor] = None) -> None:
+    if p > 0.0 and CONFIG.fold_dropout_bwd and (mask is not None or CONFIG.fold_dropout_philox):
+        _LAST_DROP.update(ptr=out.data_ptr(), numel=out.numel(), p=float(p), op_id=int(op_id), mask=mask)
 
 
 def _claim_dropout_note(x: torch.Tensor):
     note = None
     if _LAST_DROP["ptr"] and _LAST_DROP["ptr"] == x.data_ptr() and _LAST_DROP["numel"] == x.numel():
-        note = (_LAST_DROP["p"], _LAST_DROP["op_id"])
+        note = (_LAST_DROP["p"], _LAST_DROP["op_id"], _LAST_DROP["mask"])
     _LAST_DROP["ptr"] = 0
+    _LAST_DROP["mask"] = None
     return note
 
 
@@ -279,7 +290,11 @@ def _ln_backward(ctx, dy, dres):
         scratch, ticket = _ln_scratch(x.device, x.shape[-1])
         kw.update(grad_out=tgt, accumulate=GRAD_MODE["accumulate"], scratch=scratch, ticket=ticket, deterministic=CONFIG.deterministic)
     if ctx.drop is not None:
-        kw.update(drop_p=ctx.drop[0], rng=rng_state(x.device), op_id=ctx.drop[1])
+        kw.update(drop_p=ctx.drop[0], op_id=ctx.drop[1])
+        if ctx.drop[2] is not None:
+            kw.update(drop_mask=ctx.drop[2])          # keep bits recorded by the forward GEMM epilogue
+        else:
+            kw.update(rng=rng_state(x.device))        # regenerate the mask with Philox (slow inside this kernel, see CONFIG)
     dx, dw, dmask = _C.layernorm_bwd(dy.contiguous(), x, w.contiguous(), mean, rstd, dr, **kw)
     if ctx.drop is not None:
         _DROP_STASH[ctx.drop[1]] = (dx.data_ptr(), dmask)
@@ -364,15 +379,18 @@ class _LinearDropoutAdd(torch.autograd.Function):
         pe = float(p) if training else 0.0
         rng = rng_state(x.device)
         op_id = _next_op_id() if pe > 0 else 0
+        mask = None
         if _tc_ok(M, N, K):
-            out = _C.gemm(x2, w, epilogue=EPI_DROPOUT_ADD, aux_in=r2, p=pe, rng=rng, op_id=op_id)
+            mask = _new_keep_mask(M, N, x2.device, pe)
+            out = _C.gemm(x2, w, epilogue=EPI_DROPOUT_ADD, aux_in=r2, p=pe, rng=rng, op_id=op_id,
+                          **({"mask_out": mask, "two_cta": True} if mask is not None else {}))
         else:
             y = x2 @ w.t()
             out = _C.dropout_add(y, r2.contiguous(), pe, rng, op_id) if y.numel() % 8 == 0 else r2 + y
         ctx.save_for_backward(x2, w)
         ctx.meta = (x.shape, pe, op_id)
         ctx.attn = _claim_attention_note(x2)      # (heads, T) when x is the output of our attention kernel
-        _note_dropout_output(out, pe, op_id)
+        _note_dropout_output(out, pe, op_id, mask)
         return out.view(residual.shape)
 
     @staticmethod
@@ -424,14 +442,17 @@ class _MLP(torch.autograd.Function):
         else:
             z = x2 @ w1.t()
             g = _C.gelu_fwd(z) if z.numel() % 8 == 0 else torch.nn.functional.gelu(z, approximate="tanh")
+        mask = None
         if _tc_ok(M, D, H):
-            out = _C.gemm(g, w2, epilogue=EPI_DROPOUT_ADD, aux_in=r2, p=pe, rng=rng, op_id=op_id)
+            mask = _new_keep_mask(M, D, x2.device, pe)
+            out = _C.gemm(g, w2, epilogue=EPI_DROPOUT_ADD, aux_in=r2, p=pe, rng=rng, op_id=op_id,
+                          **({"mask_out": mask, "two_cta": True} if mask is not None else {}))
         else:
             y = g @ w2.t()
             out = _C.dropout_add(y, r2.contiguous(), pe, rng, op_id) if y.numel() % 8 == 0 else r2 + y
         ctx.save_for_backward(x2, w1, w2, z, g)
         ctx.meta = (x.shape, pe, op_id)
-        _note_dropout_output(out, pe, op_id)
+        _note_dropout_output(out, pe, op_id, mask)
         return out.view(residual.shape)
 
     @staticmethod
