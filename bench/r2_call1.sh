@@ -10,7 +10,7 @@ OUT=gpurun_out/bench_r2_ab.jsonl; : > $OUT
 ab() { tag=$1; shift; env "$@" timeout 600 python bench.py --steps 6 --warmup 3 2>gpurun_out/r2_bench_$tag.err | tail -1 | sed "s/^{/{\"ab\": \"$tag\", /" >> $OUT; tail -1 $OUT | cut -c1-330; }
 ab base ZTB_X=0
 ab wide ZTB_UPDATE_MODE=wide
-ab fold ZTB_FOLD_DROPOUT_BWD=1
+ab nofold ZTB_FOLD_DROPOUT_BWD=0
 ab dq16 ZTB_ATTN_DQ_BF16=1
 ab nodelta ZTB_FUSE_ATTN_DELTA=0
 ab pdl ZTB_PDL=1
