@@ -9,14 +9,13 @@ timeout 300 python bench/ln_bench.py > gpurun_out/ln_bench_r2.jsonl 2>&1; cat gp
 OUT=gpurun_out/bench_r2_ab.jsonl; : > $OUT
 ab() { tag=$1; shift; env "$@" timeout 600 python bench.py --steps 6 --warmup 3 2>gpurun_out/r2_bench_$tag.err | tail -1 | sed "s/^{/{\"ab\": \"$tag\", /" >> $OUT; tail -1 $OUT | cut -c1-330; }
 ab base ZTB_X=0
-ab wide ZTB_UPDATE_MODE=wide
 ab nofold ZTB_FOLD_DROPOUT_BWD=0
-ab dq16 ZTB_ATTN_DQ_BF16=1
-ab nodelta ZTB_FUSE_ATTN_DELTA=0
-ab pdl ZTB_PDL=1
+ab dq32 ZTB_ATTN_DQ_BF16=0
+ab nopdl ZTB_PDL=0
+ab dq32_nopdl ZTB_ATTN_DQ_BF16=0 ZTB_PDL=0
+ab carveout_all ZTB_CARVEOUT_ALL=1
+ab wide ZTB_UPDATE_MODE=wide
 ab graph ZTB_CUDA_GRAPH=1
-ab dq16_pdl ZTB_ATTN_DQ_BF16=1 ZTB_PDL=1
-ab dq16_pdl_graph ZTB_ATTN_DQ_BF16=1 ZTB_PDL=1 ZTB_CUDA_GRAPH=1
 ab base2 ZTB_X=0
 timeout 600 python bench/gap_analysis.py > gpurun_out/r2_gap.txt 2>&1; head -n 12 gpurun_out/r2_gap.txt | cut -c1-200
 timeout 600 python bench/profile_step.py > gpurun_out/step_profile.txt 2>&1; head -n 24 gpurun_out/step_profile.txt | cut -c1-160

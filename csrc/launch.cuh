@@ -17,12 +17,17 @@
 #include <utility>
 
 // An SM cannot change its L1 / shared-memory split while any CTA is resident.  The background optimizer CTAs and the flag
-// waits live for milliseconds next to the backward pass, whose tcgen05 kernels need the maximum (228 KB) carveout: if
-// such a long-lived CTA lands on an SM that a small kernel left in a small-shared configuration, the next GEMM CTA cannot
-// start there until it exits.  Every kernel of this extension therefore PREFERS the maximum carveout, so the SMs stay in
-// one configuration for the whole step (the cost: 28 KB instead of up to 228 KB of L1 for the streaming elementwise kernels,
-// which do not reuse data anyway).
-inline void ztb_prefer_max_smem(const void* fn) {
+// waits live for milliseconds next to the backward pass, whose tcgen05 kernels need the maximum (228 KB) carveout, so THOSE
+// long-lived kernels prefer the maximum carveout (force = true): they never pin an SM in a small-shared configuration.
+// Doing the same for every kernel was measured and rejected: with 28 KB of L1 left the streaming kernels slow down
+// (LayerNorm backward 56 -> 118 us, forward 23.5 -> 32 us, profiles/ln_bench_r2.jsonl); ZTB_CARVEOUT_ALL=1 restores it for A/B runs.
+inline bool ztb_carveout_all() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ZTB_CARVEOUT_ALL"); v = e ? (atoi(e) != 0) : 0; }
+  return v != 0;
+}
+inline void ztb_prefer_max_smem(const void* fn, bool force = false) {
+  if (!force && !ztb_carveout_all()) return;
   static std::mutex mu;
   static std::unordered_set<const void*> done;
   std::lock_guard<std::mutex> lock(mu);
@@ -33,7 +38,7 @@ inline bool ztb_pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("ZTB_PDL");
-    v = e ? (atoi(e) != 0) : 0;   // opt-in until the A/B run (bench/r2_call1.sh) has shown the gain on the target box
+    v = e ? (atoi(e) != 0) : 1;   // measured -3 ms per 1.3B step alone, -8 ms together with the bf16 dQ path (profiles/bench_r2_ab.jsonl)
   }
   return v != 0;
 }

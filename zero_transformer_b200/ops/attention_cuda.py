@@ -39,8 +39,17 @@ class _Attention(torch.autograd.Function):
         if delta is not None and tuple(delta.shape) != (qkv.shape[0], n_head, qkv.shape[1]):
             delta = None
         dqkv = K._C.attention_bwd(qkv, out, dout, lse, sl, n_head, scale, p, rng if p > 0 else None, op_id,
-                                  dq_bf16=K.CONFIG.attn_dq_bf16, delta=delta)
+                                  dq_bf16=_dq_bf16(qkv.shape[1]), delta=delta)
         return dqkv, None, None, None, None
+
+
+def _dq_bf16(T: int) -> bool:
+    mode = K.CONFIG.attn_dq_bf16
+    if isinstance(mode, bool):
+        return mode
+    if mode == "auto":
+        return T <= 2048 and not K.CONFIG.deterministic
+    return mode == "1"
 
 
 def alibi_attention(qkv, slopes, n_head, scale, p):

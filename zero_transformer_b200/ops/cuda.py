@@ -80,8 +80,10 @@ class _Config:
     ce_chunk_rows = int(os.environ.get("ZTB_CE_CHUNK_ROWS", "0"))   # > 0: chunked LM head + CE (logits of one chunk at a time)
     lmhead_2cta = os.environ.get("ZTB_LMHEAD_2CTA", "0") == "1"   # vocabulary-sized GEMMs on the CTA-pair kernel as well
     attn_impl = os.environ.get("ZTB_ATTN", "auto")                # auto | tc (own kernel) | flash (flash_attn library) | ref
-    # head_dim 128: accumulate dQ over key blocks directly in the bf16 dqkv buffer (no fp32 scratch, zero-fill, convert pass)
-    attn_dq_bf16 = os.environ.get("ZTB_ATTN_DQ_BF16", "0") == "1"
+    # head_dim 128: accumulate dQ over key blocks directly in the bf16 dqkv buffer (no fp32 scratch, zero-fill, convert pass).
+    # "auto" = on up to 2048 tokens (<= 16 bf16 roundings per element), fp32 scratch beyond that and in deterministic mode;
+    # measured -3.7 ms per 1.3B step (profiles/bench_r2_ab.jsonl), same loss trajectory.
+    attn_dq_bf16 = os.environ.get("ZTB_ATTN_DQ_BF16", "auto")
     # order-fixed reductions where the fast path uses atomics (LayerNorm weight gradient): bitwise run-to-run
     # reproducibility for T <= 256 (longer sequences: attention dQ has > 2 reduce-add contributions per element)
     deterministic = os.environ.get("ZTB_DETERMINISTIC", "0") == "1"
@@ -621,7 +623,7 @@ class _LMHeadLossChunked(torch.autograd.Function):
         labels[:, :-1] = tokens[:, 1:].to(torch.int32)
         labels = labels.view(-1)
         count = B * (T - 1)
-        need_grad = torch.is_grad_enabled() and (h.requires_grad or wte.requires_grad)
+        need_grad = any(ctx.needs_input_grad[:2])   # (grad mode is off inside Function.forward; this is the caller's view)
         dh = torch.empty_like(h2) if need_grad else None
         one = torch.ones(1, dtype=torch.float32, device=h.device)
         total = torch.zeros((), dtype=torch.float32, device=h.device)
