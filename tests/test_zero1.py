@@ -160,3 +160,34 @@ def test_elementwise_clip_not_global_norm():
     g = torch.tensor([10.0, 0.5, -7.0])
     adamw_step_(p, g, m, v, lr=1.0, beta1=0.9, beta2=0.95, eps=1e-8, wd=0.0, step=1, clip=1.0)
     torch.testing.assert_close(m, torch.tensor([0.1, 0.05, -0.1]))
+
+
+def test_partition_rules_drive_the_engine_layout():
+    """The regex rule table (reference ``set_partitions_zero`` / ``create_opt_spec``) is what the engine builds its shard
+    map from: buckets, decay flags and ownership all come out of ``parallel/partition.py``."""
+    import pytest
+    import torch
+
+    from zero_transformer_b200.models.gpt import GPTConfig, Transformer
+    from zero_transformer_b200.parallel import partition as P
+    from zero_transformer_b200.parallel.zero1 import Zero1Engine
+
+    m = Transformer(GPTConfig(embedding_dim=64, vocab_size=256, num_head=4, block_size=16, N=3))
+    eng = Zero1Engine(m, lr_fn=lambda s: 1e-3, backend="nccl")
+    ref = P.layout_for(m, 1)
+    assert [(r.name, r.offset, r.decay, r.bucket) for r in eng.layout.regions] == [(r.name, r.offset, r.decay, r.bucket) for r in ref.regions]
+    names = {b.name for b in eng.layout.buckets}
+    assert names == {"embed", "block0", "block1", "block2"}
+    rows = {r["name"]: r for r in P.describe(P.layout_for(m, 4))}
+    assert rows["blocks.1.ln1.weight"]["bucket"] == "embed" and rows["blocks.1.ln1.weight"]["decay"] is False
+    assert rows["blocks.2.mlp.fc_in.weight"]["bucket"] == "block2" and rows["blocks.2.mlp.fc_in.weight"]["decay"] is True
+    assert rows["wte.weight"]["spec"] == ("dp", None) and rows["wte.weight"]["rows_per_rank"] == 64.0
+    L4 = P.layout_for(m, 4)
+    assert P.owner_of(L4, "wte.weight", 0) == 0 and P.owner_of(L4, "wte.weight", 256 * 64 - 1) == 3
+    # custom rules: everything in one bucket, no decay on the embedding; an uncovered name is an error
+    rules = (P.Rule(r"^wte", bucket="all", decay=False), P.Rule(r"^(blocks|ln_f)", bucket="all"))
+    Lc = P.build_layout([(n, tuple(p.shape)) for n, p in m.named_parameters()], 2, rules=rules)
+    assert len(Lc.buckets) == 1 and not next(r for r in Lc.regions if r.name == "wte.weight").decay
+    with pytest.raises(KeyError):
+        P.build_layout([("mystery.weight", (4, 4))], 2, rules=rules)
+    assert P.main(["--model", "test", "--world", "2"]) == 0

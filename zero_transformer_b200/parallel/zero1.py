@@ -34,7 +34,8 @@ import torch
 import torch.distributed as dist
 
 from ..ops import reference
-from .layout import FlatLayout, default_bucket_of
+from . import partition
+from .layout import FlatLayout
 
 
 def _dist_info(group):
@@ -59,7 +60,7 @@ class Zero1Engine:
         compute_dtype: Optional[torch.dtype] = None,
         grad_dtype: Optional[torch.dtype] = None,
         decay_mask: Optional[Dict[str, bool]] = None,
-        bucket_of=default_bucket_of,
+        bucket_of=None,   # None: the rule table of parallel/partition.py
         ag_gemm: bool = True,
         comm_sms="auto",   # accepted for config compatibility; SM reservation was measured and dropped (round 1)
         clip_mode: str = "elementwise",
@@ -107,9 +108,10 @@ class Zero1Engine:
         self.main_grads = self.grad_dtype != self.compute_dtype
         if self.main_grads and (self.grad_dtype != torch.float32 or dev.type != "cuda"):
             raise ValueError("main gradients are fp32 next to bf16 parameters on a CUDA device")
-        if decay_mask is None:
-            decay_mask = model.decay_mask() if hasattr(model, "decay_mask") else {n: p.ndim >= 2 for n, p in named}
-        self.layout = FlatLayout([(n, tuple(p.shape)) for n, p in named], decay_mask, self.world, bucket_of)
+        if decay_mask is None and hasattr(model, "decay_mask"):
+            decay_mask = model.decay_mask()
+        # ordered regex rules -> (spec, bucket, weight decay) per parameter: the reference's set_partitions_zero / create_opt_spec
+        self.layout = partition.build_layout([(n, tuple(p.shape)) for n, p in named], self.world, decay_mask, bucket_of)
         L = self.layout
 
         if backend == "auto":
