@@ -5,6 +5,9 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# per-kernel durations: with programmatic dependent launch a kernel's CUPTI interval starts when it is scheduled, i.e. it
+# includes the time it spends in griddepcontrol.wait behind its predecessor -- profile with plain stream order
+os.environ.setdefault("ZTB_PDL", "0")
 import torch
 from torch.profiler import ProfilerActivity, profile
 

@@ -130,16 +130,17 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * D);
     const uint4* gr = reinterpret_cast<const uint4*>(dy + (size_t)row * D);
     float mu = mean[row], rs = rstd[row];
-    // Two passes over the row.  The second pass RE-LOADS x and dy (L1 / L2 hits: this warp read them a few hundred cycles
-    // ago) instead of keeping 2 x 8*NV packed registers alive across the warp reductions: 253 -> ~150 registers at
-    // D = 2048, so two of these CTAs and a background optimizer CTA share an SM.
+    // Two passes over the row with the packed bf16 x / dy held in registers in between (2 x 8*NV of them).  Re-loading them
+    // in the second pass instead (192 instead of 253 registers) was measured at 118 us vs 56 us per call at D = 2048: with
+    // 8 warps per SM the second round of load latency is fully exposed (profiles/ln_bench_r2_call2.jsonl).
+    uint4 px[NV], pg[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      uint4 ux = ld_nc_l1_v4(xr + i * 32 + lane);
-      uint4 ug = ld_nc_l1_v4(gr + i * 32 + lane);
+      px[i] = ld_nc_v4(xr + i * 32 + lane);
+      pg[i] = ld_nc_v4(gr + i * 32 + lane);
       uint4 uw = ld_v4(wr + i * 32 + lane);
-      uint32_t xs[4] = {ux.x, ux.y, ux.z, ux.w}, gs[4] = {ug.x, ug.y, ug.z, ug.w};
+      uint32_t xs[4] = {px[i].x, px[i].y, px[i].z, px[i].w}, gs[4] = {pg[i].x, pg[i].y, pg[i].z, pg[i].w};
       uint32_t ws[4] = {uw.x, uw.y, uw.z, uw.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -160,8 +161,7 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
       uint4 uw = ld_v4(wr + i * 32 + lane);
       uint4 ur = make_uint4(0, 0, 0, 0);  // gradient arriving through the residual branch (fused add)
       if (dres != nullptr) ur = ld_nc_v4(reinterpret_cast<const uint4*>(dres + (size_t)row * D) + i * 32 + lane);
-      uint4 ux = ld_nc_l1_v4(xr + i * 32 + lane), ug = ld_nc_l1_v4(gr + i * 32 + lane);
-      uint32_t xs[4] = {ux.x, ux.y, ux.z, ux.w}, gs[4] = {ug.x, ug.y, ug.z, ug.w};
+      uint32_t xs[4] = {px[i].x, px[i].y, px[i].z, px[i].w}, gs[4] = {pg[i].x, pg[i].y, pg[i].z, pg[i].w};
       uint32_t ws[4] = {uw.x, uw.y, uw.z, uw.w}, rr[4] = {ur.x, ur.y, ur.z, ur.w}, os[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
