@@ -207,6 +207,8 @@ def main():
         from zero_transformer_b200.utils.metrics import measured_peaks
 
         pk = measured_peaks()
+        fused = getattr(getattr(tr, "engine", None), "_fused", None)
+        plane = "nccl (library baseline)" if args.impl != "ours" else ("single GPU" if world == 1 else ("nvls" if getattr(fused, "nvls", False) else "p2p"))
         rec = {
             "metric": f"tokens/sec (whole box, max over ranks) GPT-2 {MODEL_LABEL.get(MODEL, MODEL)} ZeRO-1", "value": round(tok_s, 1), "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": n_warm, "cuda_graph": bool(getattr(tr, "use_graph", False)), "ms_per_step": round(ms_dev / args.steps, 3),
@@ -217,7 +219,7 @@ def main():
             "impl": args.impl,
             "config": {"model": f"gpt2-{MODEL} ALiBi (D={model_cfg.embedding_dim},H={model_cfg.num_head},N={model_cfg.N},V={model_cfg.vocab_size})",
                        "global_batch": ROWS_PER_GPU * world, "seq_len": SEQ, "grad_accum": ACCUM, "dropout": 0.1,
-                       "parallelism": f"dp{world}+zero1", "optimizer": "AdamW fp32 master, elementwise clip 1.0",
+                       "parallelism": f"dp{world}+zero1", "data_plane": plane, "optimizer": "AdamW fp32 master, elementwise clip 1.0",
                        "l2": "working set per step (weights+activations, >30 GB) far exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": round(tok_s_e2e, 1), "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss},

@@ -32,43 +32,112 @@ def key_of(d):
     return f"{m}/seq{c['seq_len']}/rows{rows}/accum{c['grad_accum']}/n{d['n_gpus']}"
 
 
+def call_no(fname):
+    m = re.search(r"call(\d+)", fname)
+    return int(m.group(1)) if m else 0
+
+
+def write_baseline_md(pairs):
+    """one row per BASELINE config, cells '1 / 2 / 4 / 8 GPUs'."""
+    path = os.path.join(ROOT, "BASELINE.md")
+    s = open(path).read()
+    if "<!-- results:begin -->" not in s:
+        return
+    cfgs = [("GPT-2 417M ALiBi bf16, seq 1024 (32 rows x 2 micro-batches / GPU)", "417m/seq1024/rows32/accum2"),
+            ("GPT-2 760M ALiBi bf16, seq 1024", "760m/seq1024/rows32/accum2"),
+            ("**GPT-2 1.3B ALiBi bf16, seq 1024 (headline)**", "1_3b/seq1024/rows32/accum2"),
+            ("GPT-2 1.3B, seq 1024, small batch (8 rows, accum 1: communication-visible)", "1_3b/seq1024/rows8/accum1"),
+            ("GPT-2 1.3B, seq 2048, accum 8 (8 x 2048-token rows per micro-batch)", "1_3b/seq2048/rows64/accum8")]
+    rows = ["| Config | GPUs | baseline (NCCL + cuBLAS + flash-attn) tok/s | ours tok/s | ratio | ours ms/step | ours e2e tok/s |", "|---|---|---|---|---|---|---|"]
+    rows.append("| test-size model, ZeRO-1 world 2, CPU / gloo (plumbing only) | 0 | - | pass (`tests/test_zero1.py`, `tests/test_train_cli.py`) | - | - | - |")
+    for label, key in cfgs:
+        ns = [n for n in (1, 2, 4, 8) if f"{key}/n{n}" in pairs]
+        if not ns:
+            rows.append(f"| {label} | - | not run | not run | - | - | - |")
+            continue
+        cell = lambda f: " / ".join(f(*pairs[f"{key}/n{n}"]) for n in ns)
+        rows.append(f"| {label} | {' / '.join(map(str, ns))} | " + cell(lambda o, b: f"{b['value'] / 1e3:.1f}k" if b else "-") + " | "
+                    + cell(lambda o, b: f"{o['value'] / 1e3:.1f}k") + " | " + cell(lambda o, b: f"{o['value'] / b['value']:.2f}x" if b else "-") + " | "
+                    + cell(lambda o, b: f"{o['ms_per_step']:.1f}") + " | " + cell(lambda o, b: f"{o.get('e2e', {}).get('value', 0) / 1e3:.1f}k") + " |")
+    comm = []
+    for f in sorted(glob.glob(os.path.join(P, "comm_bench_n*.json"))):
+        d = json.load(open(f))
+        r, nr, na = d.get("rs_adam_fused"), d.get("nccl_reduce_scatter"), d.get("nccl_all_gather")
+        if r and nr and na:
+            comm.append(f"| 1.3B gradients / parameters (2.62 GB bf16), n = {d['world']} | NCCL reduce-scatter {nr['ms']} ms ({nr['busbw_gbs']} GB/s bus) + "
+                        f"all-gather {na['ms']} ms ({na['busbw_gbs']} GB/s) | fused reduce-scatter + AdamW + all-gather, {r.get('plane', 'p2p')} plane: {r['ms']} ms "
+                        f"= {r.get('roofline_frac')} of its roofline ({r.get('bound')}-bound, {r.get('roofline_ms')} ms) |")
+    block = ["<!-- results:begin -->", *rows, ""]
+    if comm:
+        block += ["| Collective (config #5: bus bandwidth) | baseline | ours |", "|---|---|---|", *comm, ""]
+    block += ["Sources: `profiles/RESULTS.md` (per-record clocks, MFU, file names), `profiles/comm_bench_n*.json`.", "<!-- results:end -->"]
+    a, b = s.index("<!-- results:begin -->"), s.index("<!-- results:end -->") + len("<!-- results:end -->")
+    open(path, "w").write(s[:a] + "\n".join(block) + s[b:])
+
+
 def main():
-    recs = []
-    for f in sorted(glob.glob(os.path.join(P, "sweep_n*.jsonl")) + glob.glob(os.path.join(P, "bench_r2_*.jsonl"))):
+    # Throughput pairs: both arms of a row come from the SAME sweep file = the same gpurun call = the same box, minutes
+    # apart (boxes differ by ~5 % in power-capped clocks, so cross-box ratios are not quoted).  Latest call wins.
+    pairs = {}
+    for f in sorted(glob.glob(os.path.join(P, "sweep_n*.jsonl")), key=lambda f: call_no(os.path.basename(f))):
+        o, b = {}, {}
         for d in lines(f):
-            if "value" in d and "config" in d:
-                d["_file"] = os.path.basename(f)
-                recs.append(d)
+            if "value" not in d or "config" not in d:
+                continue
+            d["_file"] = os.path.basename(f)
+            if d.get("impl") == "baseline":
+                b[key_of(d)] = d
+            elif d.get("impl") == "ours" and d.get("config", {}).get("parallelism", "").endswith("zero1") and not os.environ.get("X"):
+                k = key_of(d) + ("/p2p" if d.get("config", {}).get("data_plane") == "p2p" or d.get("plane") == "p2p" else "")
+                o[k] = d
+        for k in set(o) | set(b):
+            if k in o and (k in b or k.endswith("/p2p")):
+                pairs[k] = (o[k], b.get(k))
     base = {}
-    for d in recs:
-        if d.get("impl") == "baseline":
-            k = key_of(d)
-            if k not in base or d["value"] > base[k]["value"]:
-                base[k] = {"value": d["value"], "ms_per_step": d["ms_per_step"], "e2e": d.get("e2e", {}).get("value"),
-                           "clocks": d.get("clocks"), "note": f"bench.py --impl baseline ({d['_file']})"}
+    for k, (o, b) in pairs.items():
+        if b:
+            base[k] = {"value": b["value"], "ms_per_step": b["ms_per_step"], "e2e": b.get("e2e", {}).get("value"),
+                       "clocks": b.get("clocks"), "note": f"bench.py --impl baseline ({b['_file']})"}
     if base:
         json.dump(base, open(os.path.join(P, "baseline_arm.json"), "w"), indent=1, sort_keys=True)
     out = ["# Measured results (auto-generated by bench/make_tables.py from the JSON records in this directory)", "",
            "All lines are `bench.py` records: CUDA-event timed, max over ranks, 6 timed steps after >= 3 warm-up steps, clocks sampled",
            "during the timed region (`sm_mhz` = median under load; `sw_power_cap` is normal on a 1 kW part).", "",
-           "## Throughput: ours vs the stock-library baseline arm (same pod)", "",
+           "## Throughput: ours vs the stock-library baseline arm", "",
+           "Both arms of a row were run back to back in the same gpurun call (same box).  `ratio` = ours / baseline.", "",
            "| config | GPUs | ours tok/s | ours ms/step | ours e2e tok/s | baseline tok/s | baseline ms/step | ratio | MFU (causal FLOPs, vs sustained cuBLAS) | sm MHz ours / base | source |",
            "|---|---|---|---|---|---|---|---|---|---|---|"]
-    ours = {}
-    for d in recs:
-        if d.get("impl") == "ours" and d.get("config", {}).get("parallelism", "").endswith("zero1"):
-            k = key_of(d)
-            tag = d.get("plane", "")
-            if k not in ours or d["value"] > ours[k]["value"]:
-                ours[k] = d
-    for k in sorted(set(ours) | set(base), key=lambda s: (s.split("/")[0], s.split("/")[1], s.split("/")[2], int(s.rsplit("n", 1)[1]))):
-        o, b = ours.get(k), base.get(k)
-        n = k.rsplit("n", 1)[1]
-        ratio = f"{o['value'] / b['value']:.2f}x" if o and b else ""
-        out.append(f"| `{k.rsplit('/', 1)[0]}` | {n} | {o['value'] / 1e3:.1f}k | {o['ms_per_step']} | {o.get('e2e', {}).get('value', 0) / 1e3:.1f}k | "
+
+    def order(s):
+        p = s.split("/")
+        return (p[0], p[1], p[2], int(re.search(r"n(\d+)", s).group(1)), s)
+
+    for k in sorted(pairs, key=order):
+        o, b = pairs[k]
+        n = re.search(r"/n(\d+)", k).group(1)
+        cfg = re.sub(r"/n\d+", "", k)
+        ratio = f"{o['value'] / b['value']:.2f}x" if b else ""
+        out.append(f"| `{cfg}` | {n} | {o['value'] / 1e3:.1f}k | {o['ms_per_step']} | {o.get('e2e', {}).get('value', 0) / 1e3:.1f}k | "
                    f"{(b['value'] / 1e3 if b else 0):.1f}k | {b['ms_per_step'] if b else ''} | {ratio} | {o.get('mfu_vs_measured_sustained', '')} | "
-                   f"{(o.get('clocks') or {}).get('sm_mhz')} / {((b or {}).get('clocks') or {}).get('sm_mhz')} | {o.get('_file')} |"
-                   if o else f"| `{k.rsplit('/', 1)[0]}` | {n} | | | | {b['value'] / 1e3:.1f}k | {b['ms_per_step']} | | | / {(b.get('clocks') or {}).get('sm_mhz')} | |")
+                   f"{(o.get('clocks') or {}).get('sm_mhz')} / {((b or {}).get('clocks') or {}).get('sm_mhz')} | {o.get('_file')} |")
+    # weak-scaling efficiency of the headline config, per call
+    out += ["", "## Weak scaling, headline config (tokens/s at n GPUs / (n x tokens/s at 1 GPU), best 1-GPU sweep record as the denominator)", ""]
+    head = {int(re.search(r"/n(\d+)", k).group(1)): v for k, v in pairs.items() if k.startswith("1_3b/seq1024/rows32/accum2/n") and not k.endswith("/p2p")}
+    if 1 in head:
+        o1, b1 = head[1]
+        out += ["| GPUs | ours tok/s | ours efficiency | baseline tok/s | baseline efficiency |", "|---|---|---|---|---|"]
+        for n in sorted(head):
+            o, b = head[n]
+            out.append(f"| {n} | {o['value'] / 1e3:.1f}k | {o['value'] / (n * o1['value']):.3f} | {b['value'] / 1e3:.1f}k | {b['value'] / (n * b1['value']):.3f} |")
+    # switch A/B records
+    out += ["", "## Switch A/B runs (1 GPU, headline config; each file = one call = one box, compare within a file only)", ""]
+    for f in sorted(glob.glob(os.path.join(P, "bench_r2_*.jsonl")), key=lambda f: call_no(os.path.basename(f))):
+        rows = [d for d in lines(f) if "ms_per_step" in d]
+        if rows:
+            out.append(f"* `{os.path.basename(f)}`: " + ", ".join(f"{d.get('ab', '?')} {d['ms_per_step']:.1f} ms" for d in rows)
+                       + f"  (sm {rows[0].get('clocks', {}).get('sm_mhz')} MHz)")
+    recs = [1] * (len(pairs))
+    write_baseline_md(pairs)
     out += ["", "## Communication kernels (bench/comm_bench.py)", ""]
     for f in sorted(glob.glob(os.path.join(P, "comm_bench_n*.json"))):
         d = json.load(open(f))
