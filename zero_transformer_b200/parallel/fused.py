@@ -160,16 +160,16 @@ class FusedComm:
     def _my_row(self, kind: int, bucket: int) -> int:
         return self._flags.ptrs[self.rank] + 4 * self._slot(kind, bucket, 0)
 
-    def _ev(self, value: int):
+    def _epoch_arg(self, value: int):
         """(value, value_ptr) for the flag kernels: the literal step number, or (0, &epoch_dev) in CUDA-graph mode."""
         return (0, self.epoch_dev.data_ptr()) if self.graph_mode else (int(value), 0)
 
     def _signal(self, kind: int, bucket: int, value: int) -> None:
-        v, ptr = self._ev(value)
+        v, ptr = self._epoch_arg(value)
         self._C.signal(self._flags.ptrs, self._slot(kind, bucket, self.rank), v, ptr)
 
     def _wait(self, kind: int, bucket: int, value: int) -> None:
-        v, ptr = self._ev(value)
+        v, ptr = self._epoch_arg(value)
         self._C.wait_flags(self._my_row(kind, bucket), self.world, v, ptr)
 
     def set_graph_mode(self, on: bool) -> None:
@@ -278,8 +278,8 @@ class FusedComm:
         two_cta = self.ag_two_cta and (plan0 := self.ag_plan(b, first_region, AG2_TILE))["rows_per_rank"] % 128 == 0
         plan = plan0 if two_cta else self.ag_plan(b, first_region)
         out = self._C.gemm_ag(x2, w, self._param.ptrs, self.flat_param, plan["segs"], plan["nseg"], plan["n_b"], plan["tiles"],
-                              self._my_row(FLAG_SHARD_READY, b), self._ev(self.epoch)[0], self.ag_done, plan["b_tiles"], plan["rows_per_rank"],
-                              self.world, self.rank, two_cta, self._ev(self.epoch)[1])
+                              self._my_row(FLAG_SHARD_READY, b), self._epoch_arg(self.epoch)[0], self.ag_done, plan["b_tiles"], plan["rows_per_rank"],
+                              self.world, self.rank, two_cta, self._epoch_arg(self.epoch)[1])
         self._ag_pending[b] = False
         self._pending[b] = False
         return out
