@@ -153,6 +153,7 @@ ZTB_DEVINL void mbar_arrive_cta0(uint64_t* bar) {  // arrive on CTA 0's copy of 
 constexpr int AG_TILE_ELEMS = 4096;                 // 8 KB per bulk copy
 constexpr int AG_TILE_BYTES = AG_TILE_ELEMS * 2;
 constexpr int AG_SLOTS = 4;                         // copies in flight per CTA: 148 x 32 KB covers NVLink bandwidth x latency
+constexpr int kAgMaxSegs = 32;                     // pull-list entries staged in shared memory (8 ranks x 4 matrices = 28)
 constexpr int STAGES_AG = 4;                        // the AG variant gives one operand stage (32 KB) to the gather ring
 
 struct AgParams {
@@ -324,6 +325,19 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (AG && warp == 11) {
     // ===================================================== all-gather driver (one thread per CTA, bulk copies over NVLink)
     if constexpr (AG) {
+      // The pull list is consulted three times per 8 KB copy (issue, store, publish): from global memory every lookup is a
+      // chain of dependent ~0.6 us loads and the single driver thread, not NVLink, limited the gather (measured: fused GEMM
+      // = plain GEMM + 0.8 x the standalone pull time at n = 2).  Stage the list in shared memory once.
+      __shared__ ZtbSegment seg_s[kAgMaxSegs];
+      const bool segs_staged = ag.nseg <= kAgMaxSegs;
+      if (segs_staged) {
+        const int words = ag.nseg * (int)(sizeof(ZtbSegment) / 8);
+        const unsigned long long* gsrc = reinterpret_cast<const unsigned long long*>(ag.segs);
+        unsigned long long* sdst = reinterpret_cast<unsigned long long*>(seg_s);
+        for (int i = lane; i < words; i += 32) sdst[i] = gsrc[i];
+      }
+      __syncwarp();
+      const ZtbSegment* seg_tab = segs_staged ? seg_s : ag.segs;
       if (lane == 0) {
         unsigned seen = 1u << ag.rank;
         const int want_epoch = ag.epoch + (ag.epoch_ptr != nullptr ? *ag.epoch_ptr : 0);
@@ -339,9 +353,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           int lo = 0, hi = ag.nseg - 1;
           while (lo < hi) {
             int mid = (lo + hi + 1) >> 1;
-            if (ag.segs[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
+            if (seg_tab[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
           }
-          const ZtbSegment sg = ag.segs[lo];
+          const ZtbSegment sg = seg_tab[lo];
           const long long e0 = (t - sg.tile_begin) * AG_TILE_ELEMS;
           const long long left = sg.len - e0;
           bytes = (uint32_t)((left < AG_TILE_ELEMS ? left : AG_TILE_ELEMS) * 2);
