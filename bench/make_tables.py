@@ -117,8 +117,9 @@ def main():
         n = re.search(r"/n(\d+)", k).group(1)
         cfg = re.sub(r"/n\d+", "", k)
         ratio = f"{o['value'] / b['value']:.2f}x" if b else ""
+        bval = f"{b['value'] / 1e3:.1f}k" if b else "-"
         out.append(f"| `{cfg}` | {n} | {o['value'] / 1e3:.1f}k | {o['ms_per_step']} | {o.get('e2e', {}).get('value', 0) / 1e3:.1f}k | "
-                   f"{(b['value'] / 1e3 if b else 0):.1f}k | {b['ms_per_step'] if b else ''} | {ratio} | {o.get('mfu_vs_measured_sustained', '')} | "
+                   f"{bval} | {b['ms_per_step'] if b else '-'} | {ratio} | {o.get('mfu_vs_measured_sustained', '')} | "
                    f"{(o.get('clocks') or {}).get('sm_mhz')} / {((b or {}).get('clocks') or {}).get('sm_mhz')} | {o.get('_file')} |")
     # weak-scaling efficiency of the headline config, per call
     out += ["", "## Weak scaling, headline config (tokens/s at n GPUs / (n x tokens/s at 1 GPU), best 1-GPU sweep record as the denominator)", ""]
