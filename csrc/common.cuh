@@ -288,6 +288,11 @@ ZTB_DEVINL uint4 ld_nc_v4(const void* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+ZTB_DEVINL uint32_t ld_nc_u8(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
 // read-only path WITH L1 allocation: for strided per-thread row reads where the other 16-byte pieces of
 // the same 128-byte line are consumed by the following loads of the same thread
 ZTB_DEVINL uint4 ld_nc_l1_v4(const void* p) {

@@ -108,7 +108,10 @@ ZTB_DEVINL void ln_bwd_finalize(float* dw, int D, const LnBwdExtra& ex, bool* is
   if (threadIdx.x == 0) *ex.ticket = 0u;
 }
 
-template <int NV>
+// DROP: 0 = no masked copy, 1 = keep bits from the forward epilogue, 2 = mask regenerated with Philox.  A template parameter,
+// not a run-time branch: with the mask code in the loop body ptxas no longer batched the row's 16 loads ahead of the math and the
+// plain kernel ran at half its speed (118 us vs 56 us per call at the 1.3B shape).
+template <int NV, int DROP>
 __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                             const bf16* __restrict__ w, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, bf16* __restrict__ dx,
@@ -121,11 +124,10 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
 #pragma unroll
   for (int k = 0; k < NV * 8; ++k) acc[k] = 0.f;
   const uint4* wr = reinterpret_cast<const uint4*>(w);
-  const bool drop = ex.dmask != nullptr;
   uint64_t stream = 0;
   uint32_t thr = 0;
   Philox ph(0);
-  if (drop && ex.maskbits == nullptr) { ph = Philox(ex.rng[0]); stream = ex.rng[1] * 65536ull + ex.op_id; thr = dropout_threshold(ex.p); }
+  if constexpr (DROP == 2) { ph = Philox(ex.rng[0]); stream = ex.rng[1] * 65536ull + ex.op_id; thr = dropout_threshold(ex.p); }
   for (int row = blockIdx.x * 4 + warp; row < M; row += gridDim.x * 4) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * D);
     const uint4* gr = reinterpret_cast<const uint4*>(dy + (size_t)row * D);
@@ -170,11 +172,11 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
         os[k] = pack_bf16(rs * (gf.x * wf.x - s1 - xh0 * s2) + rf.x, rs * (gf.y * wf.y - s1 - xh1 * s2) + rf.y);
       }
       st_v4(dr + i * 32 + lane, make_uint4(os[0], os[1], os[2], os[3]));
-      if (drop) {  // masked copy of the (bf16-rounded) dx, exactly what dropout_add_kernel<false> would produce from it
+      if constexpr (DROP != 0) {  // masked copy of the (bf16-rounded) dx, exactly what dropout_add_kernel<false> would produce from it
         const size_t vi = (size_t)row * (D / 8) + i * 32 + lane;
         uint32_t keep8, ms[4];
-        if (ex.maskbits != nullptr) {
-          keep8 = ex.maskbits[vi];           // 8 keep bits recorded by the forward GEMM epilogue: no RNG work here
+        if constexpr (DROP == 1) {
+          keep8 = ld_nc_u8(ex.maskbits + vi);   // 8 keep bits recorded by the forward GEMM epilogue: no RNG work here (asm load: may be hoisted above the stores, batching with the row's other loads)
         } else {
           uint4 r0 = ph.rounds<kPhiloxRounds>(2 * vi, stream), r1 = ph.rounds<kPhiloxRounds>(2 * vi + 1, stream);
           uint32_t rb[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -501,6 +503,16 @@ static int grid_for(size_t n, int block, int max_blocks) {
   return (int)(g < (size_t)max_blocks ? (g ? g : 1) : max_blocks);
 }
 
+#define LN_DISPATCH2(NV, KERNEL, X, GRID, ...)                                                 \
+  switch (NV) {                                                                                \
+    case 1: ztb_launch(KERNEL<1, X>, dim3(GRID), dim3(128), 0, st, __VA_ARGS__); break;        \
+    case 2: ztb_launch(KERNEL<2, X>, dim3(GRID), dim3(128), 0, st, __VA_ARGS__); break;        \
+    case 3: ztb_launch(KERNEL<3, X>, dim3(GRID), dim3(128), 0, st, __VA_ARGS__); break;        \
+    case 4: ztb_launch(KERNEL<4, X>, dim3(GRID), dim3(128), 0, st, __VA_ARGS__); break;        \
+    case 6: ztb_launch(KERNEL<6, X>, dim3(GRID), dim3(128), 0, st, __VA_ARGS__); break;        \
+    case 8: ztb_launch(KERNEL<8, X>, dim3(GRID), dim3(128), 0, st, __VA_ARGS__); break;        \
+  }
+
 #define LN_DISPATCH(NV, KERNEL, GRID, ...)                                                     \
   switch (NV) {                                                                                \
     case 1: ztb_launch(KERNEL<1>, dim3(GRID), dim3(128), 0, st, __VA_ARGS__); break;           \
@@ -541,7 +553,13 @@ int ztb_layernorm_bwd(const void* dy, const void* x, const void* w, const float*
   if (ex.ticket == nullptr) ZTB_CUDA_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * D, st));   // one-shot scratch: caller owns dw
   if (ln_fast(D)) {
     int nv = D / 256, grid = grid_for((M + 3) / 4, 1, sms * 4);
-    LN_DISPATCH(nv, layernorm_bwd_kernel, grid, (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, (const bf16*)dres, ex)
+    if (ex.dmask == nullptr) {
+      LN_DISPATCH2(nv, layernorm_bwd_kernel, 0, grid, (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, (const bf16*)dres, ex)
+    } else if (ex.maskbits != nullptr) {
+      LN_DISPATCH2(nv, layernorm_bwd_kernel, 1, grid, (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, (const bf16*)dres, ex)
+    } else {
+      LN_DISPATCH2(nv, layernorm_bwd_kernel, 2, grid, (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, (const bf16*)dres, ex)
+    }
   } else {
     ztb_prefer_max_smem((const void*)layernorm_bwd_generic);
     layernorm_bwd_generic<<<M, 128, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, dw, M, D, (const bf16*)dres, ex);
