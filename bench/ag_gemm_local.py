@@ -67,11 +67,21 @@ def main():
             err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
             assert torch.equal(local, full), "gather incomplete"
             assert err < 2e-2, err
-            rec["ag_2cta_ms" if two_cta else "ag_1cta_ms"] = round(timed(lambda: K._C.gemm_ag(*args)), 4)
+            done.zero_()
+            state = {"base": 0}
+            b_tiles = args[11]
+
+            def run_ag(a=args):   # cumulative landing counters: no memset launch in front of the GEMM (what FusedComm.gemm_ag does)
+                out = K._C.gemm_ag(*a, done_base=state["base"])
+                state["base"] = (state["base"] + b_tiles) & 0xFFFFFFFF
+                return out
+
+            rec["ag_2cta_ms" if two_cta else "ag_1cta_ms"] = round(timed(run_ag), 4)
+            assert torch.equal(run_ag(), out), "cumulative-counter launch differs"
             if two_cta:   # a 256-row GEMM: the kernel time is the gather's own duration (driver-thread latency chain x tiles per CTA)
                 xs = x[:256].contiguous()
                 args_s = (xs,) + args[1:]
-                rec["gather_only_ms"] = round(timed(lambda: K._C.gemm_ag(*args_s)), 4)
+                rec["gather_only_ms"] = round(timed(lambda: run_ag(args_s)), 4)
                 rec["gather_tiles_per_cta"] = round(tiles / 148, 1)
         rec["plain_2cta_ms"] = round(timed(lambda: K._C.gemm(x, wfull, two_cta=True)), 4)
         rec["plain_2cta_raster_n_ms"] = round(timed(lambda: K._C.gemm(x, wfull, two_cta=True, raster_n=1)), 4)

@@ -229,7 +229,7 @@ at::Tensor gemm(const at::Tensor& A, const at::Tensor& B, c10::optional<at::Tens
 // Forward GEMM C = A * B^T with the ZeRO-1 all-gather of B's bucket fused into the kernel.
 at::Tensor gemm_ag(const at::Tensor& A, const at::Tensor& B, std::vector<int64_t> peer_ptrs, at::Tensor& local_flat, const at::Tensor& segs,
                    int64_t nseg, int64_t n_b_segs, int64_t total_tiles, int64_t shard_ready_ptr, int64_t epoch, at::Tensor& done,
-                   int64_t b_tiles_per_rank, int64_t rows_per_rank, int64_t world, int64_t rank, bool two_cta, int64_t epoch_ptr) {
+                   int64_t b_tiles_per_rank, int64_t rows_per_rank, int64_t world, int64_t rank, bool two_cta, int64_t epoch_ptr, int64_t done_base) {
   need(is_bf16_cuda(A) && is_bf16_cuda(B) && A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "gemm_ag: A, B bf16 2-D");
   need(A.size(1) == B.size(1), "gemm_ag: K mismatch");
   need(done.is_cuda() && done.numel() >= 8 && done.element_size() == 4, "gemm_ag: done must be an 8-element 32-bit CUDA tensor");
@@ -242,7 +242,7 @@ at::Tensor gemm_ag(const at::Tensor& A, const at::Tensor& B, std::vector<int64_t
   ag.segs = reinterpret_cast<const ZtbSegment*>(segs.data_ptr()); ag.nseg = (int)nseg; ag.n_b_segs = (int)n_b_segs; ag.total_tiles = total_tiles;
   ag.shard_ready = reinterpret_cast<const int*>(shard_ready_ptr); ag.epoch = (int)epoch; ag.epoch_ptr = reinterpret_cast<const int*>(epoch_ptr);
   ag.done = reinterpret_cast<unsigned int*>(done.data_ptr()); ag.b_tiles_per_rank = (unsigned)b_tiles_per_rank;
-  ag.rows_per_rank = (int)rows_per_rank; ag.world = (int)world; ag.rank = (int)rank;
+  ag.rows_per_rank = (int)rows_per_rank; ag.world = (int)world; ag.rank = (int)rank; ag.done_base = done_base;
   ZtbGemmArgs a{};
   a.A = A.data_ptr(); a.B = B.data_ptr(); a.C = C.data_ptr();
   a.M = A.size(0); a.K = A.size(1); a.N = B.size(0);
@@ -383,7 +383,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("direct_store") = -1, py::arg("raster_n") = -1, py::arg("rowdot_out") = py::none(), py::arg("rowdot_T") = 0, py::arg("rowdot_hd") = 0, py::arg("mask_out") = py::none());
   m.def("gemm_ag", &gemm_ag, py::arg("A"), py::arg("B"), py::arg("peer_ptrs"), py::arg("local_flat"), py::arg("segs"), py::arg("nseg"),
         py::arg("n_b_segs"), py::arg("total_tiles"), py::arg("shard_ready_ptr"), py::arg("epoch"), py::arg("done"), py::arg("b_tiles_per_rank"),
-        py::arg("rows_per_rank"), py::arg("world"), py::arg("rank"), py::arg("two_cta") = false, py::arg("epoch_ptr") = 0);
+        py::arg("rows_per_rank"), py::arg("world"), py::arg("rank"), py::arg("two_cta") = false, py::arg("epoch_ptr") = 0, py::arg("done_base") = -1);
   m.def("adamw_shard", &adamw_shard, py::arg("master"), py::arg("m"), py::arg("v"), py::arg("flat_param"), py::arg("grad_ptrs"),
         py::arg("grad_is_fp32"), py::arg("segs"), py::arg("nseg"), py::arg("total_tiles"), py::arg("lr"), py::arg("beta1"), py::arg("beta2"),
         py::arg("eps"), py::arg("wd"), py::arg("clip"), py::arg("grad_scale"), py::arg("step"), py::arg("wait_flags_ptr") = 0,

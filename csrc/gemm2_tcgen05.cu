@@ -154,7 +154,8 @@ constexpr int AG_TILE_ELEMS = 4096;                 // 8 KB per bulk copy
 constexpr int AG_TILE_BYTES = AG_TILE_ELEMS * 2;
 constexpr int AG_SLOTS = 4;                         // copies in flight per CTA: 148 x 32 KB covers NVLink bandwidth x latency
 constexpr int kAgMaxSegs = 32;                     // pull-list entries staged in shared memory (8 ranks x 4 matrices = 28)
-constexpr int STAGES_AG = 4;                        // the AG variant gives one operand stage (32 KB) to the gather ring
+constexpr int STAGES_AG = 5;                        // the AG variant keeps all five operand stages (a 4-stage ring cost ~15 %) and takes the
+                                                    // gather ring's 32 KB from the epilogue staging instead: one output buffer per warp
 
 struct AgParams {
   const void* peer[8];          // flat bf16 parameter buffer of every rank (peer-mapped), index = rank
@@ -167,7 +168,7 @@ struct AgParams {
   int epoch;
   const int* epoch_ptr;         // non-null: wait for *epoch_ptr + epoch (device-side step counter, CUDA-graph replays)
   unsigned int* done;           // [8] per-owner count of landed B tiles (zeroed before launch)
-  unsigned int b_tiles_per_rank;
+  unsigned int b_tiles_per_rank;  // counter value that means "this owner's B chunk has landed" (cumulative counters: base + tiles)
   int rows_per_rank;            // B rows owned by each rank
   int world, rank;
 };
@@ -209,7 +210,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint8_t* smA = smem;
   uint8_t* smB = smem + NST * A_STAGE_BYTES;
   uint8_t* smC = smem + NST * STAGE_BYTES;
-  uint8_t* smG = smC + CSTAGE_BYTES;         // AG only: AG_SLOTS x 8 KB gather ring (the space of the fifth operand stage)
+  uint8_t* smG = smC + CSTAGE_BYTES / 2;     // AG only: AG_SLOTS x 8 KB gather ring (the second half of the epilogue staging area)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + CSTAGE_BYTES);
   uint64_t* full = bars;                     // [NST]  leader's copy collects both CTAs' TMA bytes
   uint64_t* empty = bars + STAGES;           // [NST]  multicast commit -> both CTAs
@@ -218,7 +219,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   uint64_t* gfull = bars + 2 * STAGES + 5;   // [AG_SLOTS] gather ring: bulk load landed
   uint64_t* abar = bars + 2 * STAGES + 5 + AG_SLOTS;   // [EPI_WARPS] per-warp "auxiliary operand chunk landed"
-  static_assert(AG_SLOTS * AG_TILE_BYTES == STAGE_BYTES, "the gather ring takes exactly one operand stage");
+  static_assert(AG_SLOTS * AG_TILE_BYTES == CSTAGE_BYTES / 2, "the gather ring takes exactly half of the epilogue staging area");
   static_assert((2 * STAGES + 5 + AG_SLOTS + EPI_WARPS) * 8 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -270,7 +271,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           bool fresh = false;
           for (int o = r0; o <= r1; ++o)
             if (!((owners_ready >> o) & 1u)) {
-              while ((unsigned)ld_acquire_gpu(reinterpret_cast<const int*>(ag.done + o)) < ag.b_tiles_per_rank) __nanosleep(64);
+              while ((int)((unsigned)ld_acquire_gpu(reinterpret_cast<const int*>(ag.done + o)) - ag.b_tiles_per_rank) < 0) __nanosleep(64);
               owners_ready |= 1u << o;
               fresh = true;
             }
@@ -423,7 +424,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int chalf = e >> 2;               // this warp handles 64-column chunks chalf, chalf + 2
     const int row = ew * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
-    uint8_t* wbuf = smC + e * 2 * WBUF_BYTES;   // this warp's two staging buffers
+    uint8_t* wbuf = smC + e * (AG ? 1 : 2) * WBUF_BYTES;   // this warp's two staging buffers (one in the all-gather variant)
     uint32_t thr = 0;
     uint64_t stream = 0;
     Philox ph(0);
@@ -477,7 +478,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // reading smem.  Each epilogue warp owns its 32 rows of the staging buffer and issues its own bulk stores
       // ({64|32} x 32-row boxes), so the only synchronisation is warp-local.
       auto begin_buffer = [&]() {
-        if (lane == 0) { if constexpr (kAuxTma) tma_wait_group_read<0>(); else tma_wait_group_read<1>(); }
+        if (lane == 0) { if constexpr (kAuxTma || AG) tma_wait_group_read<0>(); else tma_wait_group_read<1>(); }
         __syncwarp();
       };
       auto end_buffer = [&](const CUtensorMap* tm, int col, bool reduce) {
@@ -489,7 +490,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           else tma_store_2d(tm, src, col, m0 + ew * 32);
           tma_commit_group();
         }
-        if constexpr (!kAuxTma) cbuf ^= 1;
+        if constexpr (!kAuxTma && !AG) cbuf ^= 1;
       };
       // this thread's 16-byte piece q of half h of its auxiliary row (buffer 0, same 128-byte swizzle as the staging rows)
       auto aux_piece = [&](int h, int q) {
@@ -788,7 +789,8 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
     ag.local = (bf16*)a->local; ag.segs = a->segs; ag.nseg = a->nseg; ag.n_b_segs = a->n_b_segs; ag.total_tiles = a->total_tiles;
     ag.shard_ready = a->shard_ready; ag.epoch = a->epoch; ag.epoch_ptr = a->epoch_ptr; ag.done = a->done; ag.b_tiles_per_rank = a->b_tiles_per_rank;
     ag.rows_per_rank = a->rows_per_rank; ag.world = a->world; ag.rank = a->rank;
-    ZTB_CUDA_CHECK(cudaMemsetAsync(a->done, 0, 8 * sizeof(unsigned), st));
+    if (a->done_base < 0) ZTB_CUDA_CHECK(cudaMemsetAsync(a->done, 0, 8 * sizeof(unsigned), st));
+    else ag.b_tiles_per_rank = (unsigned)a->done_base + a->b_tiles_per_rank;   // counters are cumulative: the value that means "landed" for THIS launch
     p.raster_n = 2;
     p.nb_shift = ((a->rank * a->rows_per_rank) / BN) % p.tiles_n;
     p.full_tiles = p.num_tiles; p.tail = 0; p.split = 1; p.chain = nullptr; p.direct = 0;

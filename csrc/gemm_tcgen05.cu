@@ -145,7 +145,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (r1 >= ag.world) r1 = ag.world - 1;
           for (int o = r0; o <= r1; ++o)
             if (o != ag.rank)
-              while (ld_acquire_gpu_u32(ag.done + o) < ag.b_tiles_per_rank) __nanosleep(32);
+              while ((int)(ld_acquire_gpu_u32(ag.done + o) - ag.b_tiles_per_rank) < 0) __nanosleep(32);
           fence_proxy_async_all();  // generic-proxy stores of the gather warps -> async-proxy TMA reads
         }
         for (int kb = 0; kb < kblocks; ++kb) {
@@ -495,7 +495,8 @@ int ztb_gemm(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
     ag.local = (bf16*)a->local; ag.segs = a->segs; ag.nseg = a->nseg; ag.n_b_segs = a->n_b_segs; ag.total_tiles = a->total_tiles;
     ag.shard_ready = a->shard_ready; ag.epoch = a->epoch; ag.epoch_ptr = a->epoch_ptr; ag.done = a->done; ag.b_tiles_per_rank = a->b_tiles_per_rank;
     ag.rows_per_rank = a->rows_per_rank; ag.world = a->world; ag.rank = a->rank;
-    ZTB_CUDA_CHECK(cudaMemsetAsync(a->done, 0, 8 * sizeof(unsigned), st));
+    if (a->done_base < 0) ZTB_CUDA_CHECK(cudaMemsetAsync(a->done, 0, 8 * sizeof(unsigned), st));
+    else ag.b_tiles_per_rank = (unsigned)a->done_base + a->b_tiles_per_rank;   // counters are cumulative: the value that means "landed" for THIS launch
     p.n_major_raster = 1;
     p.nb_shift = ((a->rank * a->rows_per_rank) / BN) % p.tiles_n;
     grid = sms;  // every SM contributes a gather warp even if there are fewer tiles than SMs

@@ -64,6 +64,7 @@ struct ZtbAgArgs {              // all-gather fused into the GEMM (see AgParams 
   const ZtbSegment* segs; int nseg; int n_b_segs; long long total_tiles;
   const int* shard_ready; int epoch; const int* epoch_ptr;   // epoch_ptr != null: the awaited value is *epoch_ptr + epoch
   unsigned int* done; unsigned int b_tiles_per_rank; int rows_per_rank; int world, rank;
+  long long done_base;   // >= 0: the per-owner counters are cumulative and stood at done_base before this launch (no memset); < 0: zero them first
 };
 struct ZtbGemmArgs {
   const void* A; const void* B; void* C;   // C[M,N] = A[M,K] * B[N,K]^T  (bf16, K contiguous in both)

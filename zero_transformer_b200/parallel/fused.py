@@ -124,6 +124,7 @@ class FusedComm:
         # all-gather fused into the bucket's first GEMM: pull list with that weight's chunks first
         self.ag_lists = {}
         self.ag_done = torch.zeros(8, dtype=torch.int32, device=device)
+        self._ag_done_base = 0   # the per-owner counters are cumulative across launches (no memset per GEMM); host mirror of their value
         # CTA-pair (cta_group::2) all-gather GEMM with a bulk-copy (TMA) gather ring; 0 = the 1-CTA kernel whose gather
         # warps move the data through registers (round 1)
         self.ag_two_cta = os.environ.get("ZTB_AG_2CTA", "1") == "1"
@@ -175,6 +176,9 @@ class FusedComm:
     def set_graph_mode(self, on: bool) -> None:
         if on and not self.graph_mode:
             self.epoch_dev.fill_(self.epoch)
+        if bool(on) != self.graph_mode:   # graph mode zeroes the all-gather GEMM's landing counters per launch, eager mode lets them run
+            self.ag_done.zero_()
+            self._ag_done_base = 0
         self.graph_mode = bool(on)
 
     # per-step protocol --------------------------------------------------
@@ -279,7 +283,10 @@ class FusedComm:
         plan = plan0 if two_cta else self.ag_plan(b, first_region)
         out = self._C.gemm_ag(x2, w, self._param.ptrs, self.flat_param, plan["segs"], plan["nseg"], plan["n_b"], plan["tiles"],
                               self._my_row(FLAG_SHARD_READY, b), self._epoch_arg(self.epoch)[0], self.ag_done, plan["b_tiles"], plan["rows_per_rank"],
-                              self.world, self.rank, two_cta, self._epoch_arg(self.epoch)[1])
+                              self.world, self.rank, two_cta, self._epoch_arg(self.epoch)[1],
+                              -1 if self.graph_mode else self._ag_done_base)
+        if not self.graph_mode:   # (a captured launch cannot carry a new base: graph mode zeroes the counters instead)
+            self._ag_done_base = (self._ag_done_base + plan["b_tiles"]) & 0xFFFFFFFF
         self._ag_pending[b] = False
         self._pending[b] = False
         return out
