@@ -192,6 +192,21 @@ ZTB_DEVINL void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) 
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
 
+// L2 evict-first variants for the part of the bucket this GEMM does not consume (out-proj / fc_in / fc_out chunks): they
+// stream through without displacing the A panel the tiles re-read from L2.
+ZTB_DEVINL uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+ZTB_DEVINL void bulk_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+ZTB_DEVINL void bulk_store_1d_hint(void* gdst, const void* smem_src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(pol) : "memory");
+}
+
 template <bool A_MN, bool B_MN, int EPI, bool AG>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -347,6 +362,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const ZtbSegment* seg_tab = segs_staged ? seg_s : ag.segs;
       if (lane == 0) {
         unsigned seen = 1u << ag.rank;
+        const uint64_t evict_first = l2_evict_first_policy();
         const int want_epoch = ag.epoch + (ag.epoch_ptr != nullptr ? *ag.epoch_ptr : 0);
         // Ring of AG_SLOTS 8 KB slots.  Copy i uses slot i % AG_SLOTS: bulk-load peer -> slot (mbarrier), bulk-store
         // slot -> local buffer (bulk group).  Loads run AG_SLOTS - 1 ahead of the stores; a slot is reloaded once the
@@ -383,7 +399,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
           const int slot = (int)(i % AG_SLOTS);
           mbar_expect_tx(&gfull[slot], bytes);
-          bulk_load_1d(smG + slot * AG_TILE_BYTES, src, bytes, &gfull[slot]);
+          if (is_b) bulk_load_1d(smG + slot * AG_TILE_BYTES, src, bytes, &gfull[slot]);
+          else bulk_load_1d_hint(smG + slot * AG_TILE_BYTES, src, bytes, &gfull[slot], evict_first);
         };
         auto publish = [&](long long i) {   // store i has completed
           const bf16* src; bf16* dst; uint32_t bytes; int owner; bool is_b;
@@ -399,7 +416,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_wait(&gfull[slot], (uint32_t)((stored / AG_SLOTS) & 1));
           const bf16* src; bf16* dst; uint32_t bytes; int owner; bool is_b;
           tile_info(stored, src, dst, bytes, owner, is_b);
-          bulk_store_1d(dst, smG + slot * AG_TILE_BYTES, bytes);
+          if (is_b) bulk_store_1d(dst, smG + slot * AG_TILE_BYTES, bytes);
+          else bulk_store_1d_hint(dst, smG + slot * AG_TILE_BYTES, bytes, evict_first);
           tma_commit_group();
           if (issued < mine) {
             // copy `issued` reuses the slot that store `stored - 1` read: only the store just issued may still be reading
