@@ -60,6 +60,8 @@ def timed(fn, iters=5, warmup=2):
 
 
 def main():
+    only_ag = os.environ.get("COMM_ONLY_AG") == "1"   # quick mode: only the all-gather GEMM section
+    T = (lambda fn, **kw: float("nan")) if only_ag else timed
     env = pdist.setup_dp()
     n, r, dev = env.world, env.rank, env.device
     pk = measured_peaks()
@@ -94,7 +96,7 @@ def main():
 
     def rs_adam_record(nvls_plane):
         fc.nvls = nvls_plane
-        t = timed(fused_rs_adam)
+        t = T(fused_rs_adam)
         if nvls_plane:
             link_bytes = 2 * P * (1 + 1 / n)
             hbm_bytes = 2 * P + 24 * P / n + 2 * P
@@ -127,7 +129,7 @@ def main():
             fc.prefetch_all()
             fc.wait_all()
 
-        t = timed(ag_pull)
+        t = T(ag_pull)
         out["allgather_pull"] = {"ms": round(t, 3), "busbw_gbs": round(wire / t / 1e6, 1), "roofline_ms": round(nv, 3), "roofline_frac": round(nv / t, 3)}
 
         # standalone P2P reduce-scatter (whole model in one launch)
@@ -138,17 +140,17 @@ def main():
             C.reduce_scatter(rs_out, fc.grad_ptrs, segs, len(L.regions), tiles, 0, 0)
 
         dist.barrier()
-        t = timed(rs_p2p)
+        t = T(rs_p2p)
         out["reduce_scatter_p2p"] = {"ms": round(t, 3), "busbw_gbs": round(wire / t / 1e6, 1), "roofline_frac": round(nv / t, 3)}
 
         # NCCL on equally sized contiguous buffers
         g_in = torch.randn(L.total, device=dev).bfloat16()
         g_out = torch.empty(L.total // n, dtype=torch.bfloat16, device=dev)
-        t = timed(lambda: dist.reduce_scatter_tensor(g_out, g_in))
+        t = T(lambda: dist.reduce_scatter_tensor(g_out, g_in))
         out["nccl_reduce_scatter"] = {"ms": round(t, 3), "busbw_gbs": round(wire / t / 1e6, 1)}
-        t = timed(lambda: dist.all_gather_into_tensor(g_in, g_out))
+        t = T(lambda: dist.all_gather_into_tensor(g_in, g_out))
         out["nccl_all_gather"] = {"ms": round(t, 3), "busbw_gbs": round(wire / t / 1e6, 1)}
-        t = timed(lambda: dist.all_reduce(g_in))
+        t = T(lambda: dist.all_reduce(g_in))
         out["nccl_all_reduce"] = {"ms": round(t, 3), "busbw_gbs": round(2 * wire / t / 1e6, 1)}
 
         # all-gather fused into the QKV GEMM of one block vs. plain GEMM (+ what a separate gather costs)
@@ -182,11 +184,12 @@ def main():
                                 "vs_plain_2cta": round(t_ag / t_plain2, 3), "plain_gemm_1cta_ms": round(t_plain, 3), "plain_gemm_2cta_ms": round(t_plain2, 3),
                                 "separate_pull_ms": round(t_pull, 3), "bucket_mb": round(bucket_bytes / 1e6, 1),
                                 "roofline_ms": round(max(math_ms, nv_ms), 3), "roofline_frac": round(max(math_ms, nv_ms) / t_ag, 3),
-                                "bound": "nvlink" if nv_ms > math_ms else "math"}
+                                "bound": "nvlink" if nv_ms > math_ms else "math", "variant": os.environ.get("ZTB_AG_VARIANT", "2")}
     if env.is_main:
         print(json.dumps(out))
         os.makedirs("gpurun_out", exist_ok=True)
-        json.dump(out, open(f"gpurun_out/comm_bench_n{n}.json", "w"), indent=1)
+        if not only_ag:
+            json.dump(out, open(f"gpurun_out/comm_bench_n{n}.json", "w"), indent=1)
     pdist.shutdown()
 
 

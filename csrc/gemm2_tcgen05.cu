@@ -152,7 +152,7 @@ ZTB_DEVINL void mbar_arrive_cta0(uint64_t* bar) {  // arrive on CTA 0's copy of 
 // this rank owns; the TMA producers of the other N blocks acquire a per-owner "B chunk landed" counter first.
 constexpr int AG_TILE_ELEMS = 4096;                 // 8 KB per bulk copy
 constexpr int AG_TILE_BYTES = AG_TILE_ELEMS * 2;
-constexpr int AG_SLOTS = 4;                         // copies in flight per CTA: 148 x 32 KB covers NVLink bandwidth x latency
+constexpr int AG_SLOTS_MAX = 8;                     // gather-ring slots: 4 (AG = 1: five operand stages) or 8 (AG = 2: four stages, 7 x 8 KB copies in flight per CTA)
 constexpr int kAgMaxSegs = 32;                     // pull-list entries staged in shared memory (8 ranks x 4 matrices = 28)
 constexpr int STAGES_AG = 5;                        // the AG variant keeps all five operand stages (a 4-stage ring cost ~15 %) and takes the
                                                     // gather ring's 32 KB from the epilogue staging instead: one output buffer per warp
@@ -207,7 +207,7 @@ ZTB_DEVINL void bulk_store_1d_hint(void* gdst, const void* smem_src, uint32_t by
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(pol) : "memory");
 }
 
-template <bool A_MN, bool B_MN, int EPI, bool AG>
+template <bool A_MN, bool B_MN, int EPI, int AG>   // AG: 0 = plain, 1 / 2 = all-gather variant (see AG_SLOTS_MAX)
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
@@ -219,7 +219,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   // against 1.34 for the same GEMM without the read).  A TMA load costs that pipeline nothing; reading the row back from
   // swizzled shared memory is 4 conflict-free wavefronts per instruction.
   constexpr bool kAuxTma = EPI == ZTB_EPI_DROPOUT_ADD || EPI == ZTB_EPI_GELU_BWD || EPI == ZTB_EPI_ROWDOT;
-  constexpr int NST = AG ? STAGES_AG : STAGES;
+  constexpr int NST = AG == 2 ? STAGES - 1 : (AG ? STAGES_AG : STAGES);
+  constexpr int AG_SLOTS = AG == 2 ? 8 : 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
@@ -233,9 +234,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]       leader's copy: 8 epilogue warps (both CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   uint64_t* gfull = bars + 2 * STAGES + 5;   // [AG_SLOTS] gather ring: bulk load landed
-  uint64_t* abar = bars + 2 * STAGES + 5 + AG_SLOTS;   // [EPI_WARPS] per-warp "auxiliary operand chunk landed"
-  static_assert(AG_SLOTS * AG_TILE_BYTES == CSTAGE_BYTES / 2, "the gather ring takes exactly half of the epilogue staging area");
-  static_assert((2 * STAGES + 5 + AG_SLOTS + EPI_WARPS) * 8 <= 256, "barrier block");
+  uint64_t* abar = bars + 2 * STAGES + 5 + AG_SLOTS_MAX;   // [EPI_WARPS] per-warp "auxiliary operand chunk landed"
+  static_assert(AG_SLOTS * AG_TILE_BYTES == CSTAGE_BYTES / 2 + (STAGES - NST) * STAGE_BYTES || !AG, "the gather ring takes half of the epilogue staging area (+ one operand stage for AG = 2)");
+  static_assert((2 * STAGES + 5 + AG_SLOTS_MAX + EPI_WARPS) * 8 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -684,7 +685,7 @@ using namespace ztb;
 int ztb_make_tmap_2d(CUtensorMap* tm, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
                      int box_cols, int box_rows);
 
-template <bool A_MN, bool B_MN, int EPI, bool AG = false>
+template <bool A_MN, bool B_MN, int EPI, int AG = 0>
 static int launch2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& x, const CUtensorMap& xin,
                    const g2::GemmParams& p, int grid, cudaStream_t st, const g2::AgParams* agp = nullptr) {
   auto kern = g2::gemm2_tcgen05_kernel<A_MN, B_MN, EPI, AG>;
@@ -812,7 +813,9 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
     p.raster_n = 2;
     p.nb_shift = ((a->rank * a->rows_per_rank) / BN) % p.tiles_n;
     p.full_tiles = p.num_tiles; p.tail = 0; p.split = 1; p.chain = nullptr; p.direct = 0;
-    return launch2<false, false, ZTB_EPI_NONE, true>(ta, tb, tc, tx, tin, p, pairs * 2, st, &ag);
+    static const int ag_variant = [] { const char* e = getenv("ZTB_AG_VARIANT"); return e ? atoi(e) : 2; }();
+    if (ag_variant == 1) return launch2<false, false, ZTB_EPI_NONE, 1>(ta, tb, tc, tx, tin, p, pairs * 2, st, &ag);
+    return launch2<false, false, ZTB_EPI_NONE, 2>(ta, tb, tc, tx, tin, p, pairs * 2, st, &ag);
   }
   if (p.tail > 0 && g->epilogue == ZTB_EPI_NONE && !g->no_split) {
     float best = 1.f;
