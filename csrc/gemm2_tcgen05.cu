@@ -813,7 +813,7 @@ int ztb_gemm_2cta(const ZtbGemmArgs* g, int sms, cudaStream_t st) {
     p.raster_n = 2;
     p.nb_shift = ((a->rank * a->rows_per_rank) / BN) % p.tiles_n;
     p.full_tiles = p.num_tiles; p.tail = 0; p.split = 1; p.chain = nullptr; p.direct = 0;
-    static const int ag_variant = [] { const char* e = getenv("ZTB_AG_VARIANT"); return e ? atoi(e) : 2; }();
+    static const int ag_variant = [] { const char* e = getenv("ZTB_AG_VARIANT"); return e ? atoi(e) : 1; }();   // measured over NVLink at n = 2: variant 1 0.310 ms, variant 2 0.337 ms (plain GEMM 0.260)
     if (ag_variant == 1) return launch2<false, false, ZTB_EPI_NONE, 1>(ta, tb, tc, tx, tin, p, pairs * 2, st, &ag);
     return launch2<false, false, ZTB_EPI_NONE, 2>(ta, tb, tc, tx, tin, p, pairs * 2, st, &ag);
   }
