@@ -18,7 +18,6 @@ stack: all-reduce+slice -> reduce-scatter is the only liberty taken, in the base
 from __future__ import annotations
 
 import math
-import os
 from typing import Dict
 
 import torch

@@ -43,9 +43,6 @@ def test_train_resume_export_generate(tmp_path):
 def _uneven_worker(rank, world, port, root, out):
     import os
 
-    import numpy as np
-    import torch.distributed as dist
-
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     from zero_transformer_b200.config import DEFAULT_MODEL_CFG, load_config
     from zero_transformer_b200.parallel import dist as pdist

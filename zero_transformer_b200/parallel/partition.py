@@ -140,8 +140,6 @@ def describe(layout: FlatLayout, dtype_bytes: int = 2) -> List[dict]:
 def main(argv=None) -> int:
     import argparse
 
-    import torch
-
     from ..config import DEFAULT_MODEL_CFG
     from ..models.gpt import model_getter
 

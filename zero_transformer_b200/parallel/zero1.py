@@ -35,7 +35,6 @@ import torch.distributed as dist
 
 from ..ops import reference
 from . import partition
-from .layout import FlatLayout
 
 
 def _dist_info(group):
