@@ -7,6 +7,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("ZTB_PDL", "0")   # with PDL a kernel's interval starts before its predecessor ends: gaps would be negative
 import torch
 from torch.profiler import ProfilerActivity, profile
 

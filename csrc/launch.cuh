@@ -19,8 +19,8 @@
 // An SM cannot change its L1 / shared-memory split while any CTA is resident.  The background optimizer CTAs and the flag
 // waits live for milliseconds next to the backward pass, whose tcgen05 kernels need the maximum (228 KB) carveout, so THOSE
 // long-lived kernels prefer the maximum carveout (force = true): they never pin an SM in a small-shared configuration.
-// Doing the same for every kernel was measured and rejected: with 28 KB of L1 left the streaming kernels slow down
-// (LayerNorm backward 56 -> 118 us, forward 23.5 -> 32 us, profiles/ln_bench_r2.jsonl); ZTB_CARVEOUT_ALL=1 restores it for A/B runs.
+// Doing the same for every kernel (ZTB_CARVEOUT_ALL=1) was measured within +-1 ms of this default on the 1.3B step
+// (profiles/bench_r2_ab_call{3,10}.jsonl); it stays off so the streaming kernels keep their L1.
 inline bool ztb_carveout_all() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("ZTB_CARVEOUT_ALL"); v = e ? (atoi(e) != 0) : 0; }
