@@ -528,3 +528,119 @@ def test_gemm_dropout_epilogue_records_keep_bits(K):
     dx, _, dm = K._C.layernorm_bwd(dy, x, w, mean, rstd, None, drop_p=p, op_id=9, drop_mask=mask)
     want = K._C.dropout_add(dx, None, p, rng, 9)
     assert torch.equal(dm, want)
+
+
+# ------------------------------------------------------------------ cross-rank kernels on ONE GPU ("fake world")
+# The peer pointers of the communication kernels are plain device addresses: pointing them at other buffers of the same
+# GPU runs exactly the code the multi-GPU data plane runs (pull lists, rotated peer order, flag protocol, gather ring,
+# landing counters) -- so the single-GPU suite, compute-sanitizer included, covers comm.cu / optim.cu / the all-gather GEMM.
+# NVLink itself and the multicast (NVLS) path are covered by tests/test_multigpu.py.
+def _fake_world(W, D=256):
+    from zero_transformer_b200.parallel.layout import FlatLayout
+
+    shapes = [("blocks.0.attn.qkv.weight", (3 * D, D)), ("blocks.0.attn.out.weight", (D, D)),
+              ("blocks.0.mlp.fc_in.weight", (4 * D, D)), ("blocks.0.mlp.fc_out.weight", (D, 4 * D)), ("blocks.0.ln1.weight", (D,))]
+    return FlatLayout(shapes, {}, W, bucket_of=lambda n: "b")
+
+
+@pytest.mark.parametrize("W", [2, 4, 8])
+def test_comm_kernels_fake_world(K, W):
+    from zero_transformer_b200.parallel.fused import COPY_TILE, pack_segments
+
+    C = K._C
+    L = _fake_world(W)
+    full = _rand(L.total, scale=0.1)
+    # rank r's buffer holds only its own chunks; the rest is poison
+    bufs = []
+    for r in range(W):
+        b = torch.full((L.total,), float("nan"), dtype=torch.bfloat16, device="cuda")
+        for rg in L.regions:
+            s, e = rg.chunk_range(r)
+            b[s:e] = full[s:e]
+        bufs.append(b)
+    ptrs = [b.data_ptr() for b in bufs]
+    # all-gather pull for "rank 0" in the rotated peer order the engine uses
+    pl = [(rg.offset + p * rg.chunk, 0, rg.chunk, p) for p in range(1, W) for rg in L.regions]
+    segs, tiles = pack_segments(pl, "cuda", COPY_TILE)
+    C.allgather_pull(bufs[0], ptrs, segs, len(pl), tiles, 0, 0)
+    assert torch.equal(bufs[0], full)
+
+    # reduce-scatter into rank 0's shard: sum over every rank's copy of chunk 0 of each region
+    grads = [_rand(L.total, scale=1.0) for _ in range(W)]
+    rs = [(rg.offset, rg.shard_offset, rg.chunk, 0) for rg in L.regions]
+    segs, tiles = pack_segments(rs, "cuda", 2048)
+    out = torch.empty(L.shard_total, dtype=torch.bfloat16, device="cuda")
+    C.reduce_scatter(out, [g.data_ptr() for g in grads], segs, len(rs), tiles, 0, 0)
+    want = torch.cat([torch.stack([g[rg.offset:rg.offset + rg.chunk].float() for g in grads]).sum(0) for rg in L.regions])
+    _close(out, want, rtol=1e-2, atol=1e-2)
+
+    # flag protocol: signal writes `value` into slot `s` of every rank's pad; wait_flags returns once a row has reached it
+    pads = [torch.zeros(64, dtype=torch.int32, device="cuda") for _ in range(W)]
+    for src in range(W):
+        C.signal([p.data_ptr() for p in pads], 8 + src, 5)
+    torch.cuda.synchronize()
+    for p in pads:
+        assert torch.all(p[8:8 + W] == 5) and int(p.sum()) == 5 * W
+    C.wait_flags(pads[0].data_ptr() + 4 * 8, W, 5)       # row of W flags starting at slot 8
+    epoch = torch.full((1,), 4, dtype=torch.int32, device="cuda")
+    C.wait_flags(pads[0].data_ptr() + 4 * 8, W, 1, epoch.data_ptr())   # device-side epoch (CUDA-graph mode): 4 + 1
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("W", [2, 8])
+def test_fused_reduce_scatter_adamw_fake_world(K, W):
+    """The P2P data plane's update kernel: sum `W` gradient buffers (peer loads), scale, clip, AdamW, bf16 working copy."""
+    from zero_transformer_b200.ops.reference import adamw_step_
+    from zero_transformer_b200.parallel.fused import pack_segments
+
+    L = _fake_world(W)
+    grads = [(torch.round(torch.randn(L.total, device="cuda") * 8) / 16).bfloat16() for _ in range(W)]   # exact sums in any order
+    master = torch.randn(L.shard_total, device="cuda")
+    m, v = torch.zeros_like(master), torch.zeros_like(master)
+    flat_param = torch.zeros(L.total, dtype=torch.bfloat16, device="cuda")
+    segs, tiles = pack_segments([(rg.offset, rg.shard_offset, rg.chunk, int(rg.decay)) for rg in L.regions], "cuda")
+    pm, mm, vv = master.clone(), m.clone(), v.clone()
+    wd = torch.cat([torch.full((rg.chunk,), 0.1 if rg.decay else 0.0) for rg in L.regions]).cuda()
+    for step in (1, 2):
+        K._C.adamw_shard(master, m, v, flat_param, [g.data_ptr() for g in grads], False, segs, len(L.regions), tiles,
+                         1e-2, 0.9, 0.95, 1e-8, 0.1, 1.0, 1.0 / W, step, 0, 0)
+        g_sh = torch.cat([torch.stack([g[rg.offset:rg.offset + rg.chunk].float() for g in grads]).sum(0) for rg in L.regions])
+        adamw_step_(pm, g_sh, mm, vv, lr=1e-2, beta1=0.9, beta2=0.95, eps=1e-8, wd=wd, step=step, clip=1.0, grad_scale=1.0 / W)
+    torch.testing.assert_close(master, pm, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(v, vv, rtol=1e-5, atol=1e-8)
+    got = torch.cat([flat_param[rg.offset:rg.offset + rg.chunk] for rg in L.regions])
+    assert torch.equal(got, master.bfloat16())
+
+
+@pytest.mark.parametrize("W,two_cta", [(2, True), (8, True), (4, False)])
+def test_allgather_gemm_fake_world(K, W, two_cta):
+    """All-gather fused into the QKV GEMM with local buffers as peers: the gathered bucket must be complete and the GEMM
+    must equal x @ W_full^T although rank 0 starts with only its own chunks (twice: cumulative landing counters)."""
+    from zero_transformer_b200.parallel.fused import AG2_TILE, COPY_TILE, MAX_RANKS, pack_segments
+
+    D, M = 1024, 2048
+    L = _fake_world(W, D)
+    full = _rand(L.total, scale=0.05)
+    peers = [full.clone() for _ in range(W)]
+    local = peers[0]
+    r0 = L.regions[0]
+    x = _rand(M, D, scale=0.5)
+    flags = torch.ones(MAX_RANKS, dtype=torch.int32, device="cuda")
+    done = torch.zeros(8, dtype=torch.int32, device="cuda")
+    tile = AG2_TILE if two_cta else COPY_TILE
+    pl = [(r0.offset + p * r0.chunk, 0, r0.chunk, p) for p in range(1, W)]
+    n_b = len(pl)
+    pl += [(rg.offset + p * rg.chunk, 0, rg.chunk, p) for p in range(1, W) for rg in L.regions[1:]]
+    segs, tiles = pack_segments(pl, "cuda", tile)
+    b_tiles = (r0.chunk + tile - 1) // tile
+    ref = x.float() @ full[r0.offset:r0.offset + r0.numel].view(3 * D, D).float().t()
+    base = 0
+    for it in range(2):
+        for rg in L.regions:   # wipe everything rank 0 does not own
+            local[rg.offset + rg.chunk:rg.offset + rg.padded] = float("nan")
+        w = local[r0.offset:r0.offset + r0.numel].view(3 * D, D)
+        out = K._C.gemm_ag(x, w, [t.data_ptr() for t in peers], local, segs, len(pl), n_b, tiles, flags.data_ptr(), 1, done,
+                           b_tiles, r0.chunk // D, W, 0, two_cta, 0, base)
+        base += b_tiles
+        assert torch.equal(local, full), "gather incomplete"
+        _close(out, ref, rtol=2e-2, atol=2e-2)
