@@ -77,3 +77,36 @@ def test_extend_params_doubles_depth():
     assert torch.equal(out["wte.weight"], src["wte.weight"])
     with pytest.raises(ValueError):
         extend_params(src, 7)
+
+
+def test_make_tables_pairs_arms_per_call_and_fills_baseline_md(tmp_path, monkeypatch):
+    """bench/make_tables.py: both arms of a ratio come from the same sweep file (= same box), the latest call wins, and
+    BASELINE.md's generated block lists every GPU count that has records."""
+    import importlib
+    import json
+    import sys
+
+    def rec(impl, n, value, model="1_3b", rows=32, accum=2, plane=None):
+        return {"impl": impl, "value": value, "ms_per_step": 1.0, "n_gpus": n, "e2e": {"value": value},
+                "config": {"model": f"gpt2-{model} ALiBi", "global_batch": rows * n, "seq_len": 1024, "grad_accum": accum,
+                           "parallelism": f"dp{n}+zero1", "data_plane": plane or "nvls"}, "clocks": {"sm_mhz": 1500}}
+
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    (prof / "sweep_n1_call1.jsonl").write_text("\n".join(json.dumps(r) for r in [rec("ours", 1, 100.0), rec("baseline", 1, 80.0)]))
+    (prof / "sweep_n1_call2.jsonl").write_text("\n".join(json.dumps(r) for r in [rec("ours", 1, 130.0), rec("baseline", 1, 100.0), "garbage line"]))
+    (prof / "sweep_n8_call3.jsonl").write_text("\n".join(json.dumps(r) for r in [rec("ours", 8, 1000.0), rec("baseline", 8, 800.0), rec("ours", 8, 990.0, plane="p2p")]))
+    md = tmp_path / "BASELINE.md"
+    md.write_text("head\n<!-- results:begin -->\nold\n<!-- results:end -->\ntail\n")
+    monkeypatch.setenv("ZTB_PROFILES_DIR", str(prof))
+    monkeypatch.setenv("ZTB_BASELINE_MD", str(md))
+    sys.modules.pop("bench.make_tables", None)
+    mt = importlib.import_module("bench.make_tables")
+    mt.main()
+    base = json.load(open(prof / "baseline_arm.json"))
+    assert base["1_3b/seq1024/rows32/accum2/n1"]["value"] == 100.0 and base["1_3b/seq1024/rows32/accum2/n8"]["value"] == 800.0
+    res = (prof / "RESULTS.md").read_text()
+    assert "1.30x" in res and "1.25x" in res and "/p2p" in res and "| 8 | 1.0k | 0.962 |" in res
+    out = md.read_text()
+    assert "old" not in out and "1 / 8" in out and "1.30x / 1.25x" in out and out.startswith("head") and out.rstrip().endswith("tail")
+    sys.modules.pop("bench.make_tables", None)
