@@ -613,9 +613,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  float2 zf = unpack_bf16(us[k]);
-                  v[q * 8 + 2 * k] *= gelu_tanh_grad(zf.x);
-                  v[q * 8 + 2 * k + 1] *= gelu_tanh_grad(zf.y);
+                  const float2 gr = gelu_tanh_grad_pair(us[k]);   // packed fp16 evaluation (common.cuh)
+                  v[q * 8 + 2 * k] *= gr.x;
+                  v[q * 8 + 2 * k + 1] *= gr.y;
                 }
               }
             }
