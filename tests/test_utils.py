@@ -110,3 +110,21 @@ def test_make_tables_pairs_arms_per_call_and_fills_baseline_md(tmp_path, monkeyp
     out = md.read_text()
     assert "old" not in out and "1 / 8" in out and "1.30x / 1.25x" in out and out.startswith("head") and out.rstrip().endswith("tail")
     sys.modules.pop("bench.make_tables", None)
+
+
+def test_attention_dq_mode_auto_rule(monkeypatch):
+    """bf16 dQ accumulation: auto = up to 2048 tokens and not in deterministic mode; "0" / "1" force."""
+    from zero_transformer_b200.ops import attention_cuda as A
+    from zero_transformer_b200.ops import cuda as K
+
+    monkeypatch.setattr(K.CONFIG, "attn_dq_bf16", "auto", raising=False)
+    monkeypatch.setattr(K.CONFIG, "deterministic", False, raising=False)
+    assert A._dq_bf16(1024) and A._dq_bf16(2048) and not A._dq_bf16(4096)
+    monkeypatch.setattr(K.CONFIG, "deterministic", True, raising=False)
+    assert not A._dq_bf16(1024)
+    monkeypatch.setattr(K.CONFIG, "attn_dq_bf16", "1", raising=False)
+    assert A._dq_bf16(8192)
+    monkeypatch.setattr(K.CONFIG, "attn_dq_bf16", "0", raising=False)
+    assert not A._dq_bf16(128)
+    monkeypatch.setattr(K.CONFIG, "attn_dq_bf16", True, raising=False)   # benches set a bool
+    assert A._dq_bf16(8192)
